@@ -1,0 +1,298 @@
+"""Public-tree compiler: betting machine -> abstract betting tree -> depth-sorted SoA arrays ("flat tree").
+
+The reference builds its tree by deep-copying env state dicts while stepping a PokerEnv through every legal
+action and every board (`PokerRL/game/_/tree/PublicTree.py:111-293`).  Betting legality never depends on cards,
+so here the betting machine (`hu_engine.HUBetting`) is enumerated ONCE into an *abstract* tree whose chance nodes
+have a single "any board" child, and the abstract tree is then expanded over the board tables with vectorised
+index arithmetic.  The result has exactly the reference's nodes, child order (`allowed_actions` ascending,
+PublicTree.py:239; boards in ascending 1D-card order, :193-203) and pots, laid out for the GPU:
+
+  * nodes sorted by depth (level-synchronous sweeps), `level_start[d]` .. `level_start[d+1]`
+  * the children of a node are CONTIGUOUS (`first_child`, `n_children`) so child vectors coalesce
+  * every child of a decision node owns one row ("slot") of the regret / strategy / average-strategy tables;
+    the rows of one decision node are contiguous (`first_slot`)
+  * `dfs[n]` = index of node n in the reference's DFS pre-order (used only by parity tests / exports)
+
+Node kinds (`kind`): 0/1 = player 0/1 acts, 2 = chance acts next (reference: PlayerActionNode with
+p_id_acting_next == "Ch"), 3 = fold terminal, 4 = showdown on the final street, 5 = all-in showdown before the
+board is complete (`ValueFiller.py:34-62`).
+"""
+from itertools import combinations
+
+import numpy as np
+
+from pokerrl_b200.game import hu_engine as eng
+from pokerrl_b200.game.Poker import Poker
+
+KIND_P0, KIND_P1, KIND_CHANCE, KIND_FOLD, KIND_SHOWDOWN, KIND_SHOWDOWN_ALLIN = 0, 1, 2, 3, 4, 5
+
+
+class _Abs:
+    __slots__ = ("kind", "acted_last", "action", "pot", "round", "stack", "bet", "children", "parent", "depth",
+                 "cdepth", "allowed")
+
+
+def enumerate_betting_tree(betting, root_state=None, stop_at_street=None):
+    """DFS over the card-free betting machine. Returns the list of abstract nodes (index 0 = root)."""
+    nodes = []
+    stop = (betting.last_round + 1) if stop_at_street is None else stop_at_street
+
+    def new(kind, acted_last, action, st, parent, depth, cdepth):
+        n = _Abs()
+        n.kind, n.acted_last, n.action = kind, acted_last, action
+        n.pot, n.round = st.main_pot, st.round
+        n.stack, n.bet = tuple(st.stack), tuple(st.bet)
+        n.children, n.parent, n.depth, n.cdepth, n.allowed = [], parent, depth, cdepth, []
+        nodes.append(n)
+        return len(nodes) - 1
+
+    s0 = betting.reset() if root_state is None else root_state.copy()
+    root = new(s0.cur, -2, -1, s0, -1, 0, 0)
+    work = [(root, s0)]
+    while work:
+        i, st = work.pop()
+        me = nodes[i]
+        if stop <= st.round:
+            continue
+        me.allowed = betting.legal_actions(st)
+        pend = []
+        for a in me.allowed:
+            s = st.copy()
+            out, pre = betting.step(s, a)
+            if out == eng.CONTINUE:
+                c = new(s.cur, st.cur, a, s, i, me.depth + 1, me.cdepth)
+                pend.append((c, s))
+            elif out == eng.NEXT_ROUND:
+                # "Ch" node: state before money moves, round still the parent's (PublicTree.py:254-267)
+                c = new(KIND_CHANCE, st.cur, a, pre, i, me.depth + 1, me.cdepth)
+                # its single abstract child = first node of the new round (one per board after expansion)
+                cc = new(s.cur, -1, -1, s, c, me.depth + 2, me.cdepth + 1)
+                nodes[c].children.append(cc)
+                pend.append((cc, s))
+            else:
+                kind = {eng.FOLDED: KIND_FOLD, eng.SHOWDOWN: KIND_SHOWDOWN, eng.ALLIN_RUNDOWN: KIND_SHOWDOWN_ALLIN}[out]
+                if kind == KIND_SHOWDOWN_ALLIN and st.round == betting.last_round:
+                    kind = KIND_SHOWDOWN  # both all-in on the final street: plain showdown
+                s.round = st.round  # terminal keeps the parent's round (PublicTree.py:244-251)
+                c = new(kind, st.cur, a, s, i, me.depth + 1, me.cdepth)
+            me.children.append(c)
+        work.extend(reversed(pend))
+    return nodes
+
+
+def make_board_tables(rules, n_cdepth, root_board=()):
+    """Boards per chance depth. boards[c] = int8 [nb_c, n_cards_out]; board_parent[c] = int32 [nb_c];
+    children of one parent board are contiguous and ascend in (combination-)lexicographic card order."""
+    deck = rules.N_CARDS_IN_DECK
+    boards = [np.array([list(root_board)], dtype=np.int8).reshape(1, len(root_board))]
+    parents = [np.zeros(1, np.int32)]
+    first_round = {0: Poker.PREFLOP, rules.N_FLOP_CARDS: Poker.FLOP,
+                   rules.N_FLOP_CARDS + rules.N_TURN_CARDS: Poker.TURN}.get(len(root_board), Poker.PREFLOP)
+    rnd = first_round
+    for c in range(1, n_cdepth + 1):
+        rnd += 1
+        k = rules.n_cards_dealt_in_transition_to(rnd)
+        prev = boards[-1]
+        rows, par = [], []
+        for j in range(prev.shape[0]):
+            used = set(prev[j].tolist())
+            free = [x for x in range(deck) if x not in used]
+            for combo in combinations(free, k):
+                rows.append(list(prev[j]) + list(combo))
+                par.append(j)
+        boards.append(np.array(rows, dtype=np.int8).reshape(len(rows), prev.shape[1] + k))
+        parents.append(np.array(par, dtype=np.int32))
+    return boards, parents
+
+
+class FlatTree:
+    """Depth-sorted structure-of-arrays public tree (host numpy; uploaded to HBM by the solver)."""
+
+    def __init__(self, game_cls, env_args, stop_at_street=None, board_tables=None):
+        self.game_cls = game_cls
+        self.rules = game_cls.RULES
+        self.R = self.rules.RANGE_SIZE
+        self.betting = eng.HUBetting(game_cls, env_args)
+        self.abs_nodes = enumerate_betting_tree(self.betting, stop_at_street=stop_at_street)
+        self._expand(board_tables)
+
+    # ------------------------------------------------------------------
+    def _expand(self, board_tables):
+        A = self.abs_nodes
+        nA = len(A)
+        a_kind = np.array([n.kind for n in A], np.int8)
+        a_parent = np.array([n.parent for n in A], np.int64)
+        a_depth = np.array([n.depth for n in A], np.int64)
+        a_cdepth = np.array([n.cdepth for n in A], np.int64)
+        a_nch = np.array([len(n.children) for n in A], np.int64)
+        n_cd = int(a_cdepth.max())
+        if board_tables is None:
+            board_tables = make_board_tables(self.rules, n_cd)
+        self.boards, self.board_parent = board_tables
+        nb = np.array([b.shape[0] for b in self.boards], np.int64)
+        fan = np.ones(n_cd + 1, np.int64)  # children boards per parent board, per chance depth
+        for c in range(1, n_cd + 1):
+            fan[c] = nb[c] // nb[c - 1]
+            assert fan[c] * nb[c - 1] == nb[c]
+        board_off = np.concatenate([[0], np.cumsum(nb)])  # global board id = board_off[c] + j
+        self.board_off = board_off
+
+        # sibling groups: one per abstract non-leaf parent, plus the root's own group
+        a_k = np.zeros(nA, np.int64)  # index within sibling group
+        a_m = np.ones(nA, np.int64)  # sibling group size
+        for n in A:
+            for k, c in enumerate(n.children):
+                a_k[c] = k
+                a_m[c] = len(n.children)
+        # expanded subtree sizes (reference DFS numbering)
+        size = np.ones(nA, np.int64)
+        order = np.argsort(-a_depth, kind="stable")
+        for i in order:
+            n = A[i]
+            if n.kind == KIND_CHANCE:
+                size[i] = 1 + (fan[n.cdepth + 1] * size[n.children[0]] if n.children else 0)
+            else:
+                size[i] = 1 + sum(size[c] for c in n.children)
+        a_reloff = np.zeros(nA, np.int64)  # DFS offset relative to parent (chance children: + j_local*size)
+        for n in A:
+            off = 1
+            for c in n.children:
+                a_reloff[c] = off
+                off += size[c]
+
+        # flat ids: levels = abstract depth; inside a level, groups in order of their parent abstract node
+        max_depth = int(a_depth.max())
+        a_base = np.zeros(nA, np.int64)  # base flat id of the sibling group of abstract node a
+        level_start = [0]
+        cursor = 0
+        by_depth = [[] for _ in range(max_depth + 1)]
+        for i, n in enumerate(A):
+            by_depth[n.depth].append(i)
+        for d in range(max_depth + 1):
+            seen_parent = {}
+            for i in by_depth[d]:  # DFS creation order keeps siblings adjacent & parents in order
+                p = A[i].parent
+                if p not in seen_parent:
+                    seen_parent[p] = cursor
+                    cursor += a_m[i] * nb[a_cdepth[i]]
+                a_base[i] = seen_parent[p]
+            level_start.append(cursor)
+        N = cursor
+        self.n_nodes = int(N)
+        self.level_start = np.array(level_start, np.int64)
+        self.n_levels = max_depth + 1
+
+        parent = np.full(N, -1, np.int32)
+        first_child = np.full(N, -1, np.int32)
+        n_children = np.zeros(N, np.int32)
+        kind = np.zeros(N, np.int8)
+        acted_last = np.zeros(N, np.int8)
+        action = np.full(N, -1, np.int32)
+        pot = np.zeros(N, np.int64)
+        rnd = np.zeros(N, np.int8)
+        board = np.full(N, -1, np.int32)
+        abs_id = np.zeros(N, np.int32)
+        stack = np.zeros((N, 2), np.int64)
+        bet = np.zeros((N, 2), np.int64)
+        dfs_rel = np.zeros(N, np.int64)
+
+        a_pot = np.array([n.pot for n in A], np.int64)
+        a_round = np.array([n.round for n in A], np.int8)
+        a_acted = np.array([n.acted_last for n in A], np.int8)
+        a_action = np.array([n.action for n in A], np.int32)
+        a_stack = np.array([n.stack for n in A], np.int64)
+        a_bet = np.array([n.bet for n in A], np.int64)
+        a_first_child_abs = np.array([n.children[0] if n.children else -1 for n in A], np.int64)
+
+        for c in range(n_cd + 1):
+            sel = np.nonzero(a_cdepth == c)[0]
+            if sel.size == 0:
+                continue
+            J = np.arange(nb[c], dtype=np.int64)[None, :]
+            ids = a_base[sel][:, None] + J * a_m[sel][:, None] + a_k[sel][:, None]  # [n_sel, nb_c]
+            flat = ids.ravel()
+            rep = lambda v: np.repeat(v[sel], nb[c])  # noqa: E731
+            kind[flat] = rep(a_kind)
+            acted_last[flat] = rep(a_acted)
+            pot[flat] = rep(a_pot)
+            rnd[flat] = rep(a_round)
+            abs_id[flat] = np.repeat(sel.astype(np.int32), nb[c])
+            stack[flat] = np.repeat(a_stack[sel], nb[c], axis=0)
+            bet[flat] = np.repeat(a_bet[sel], nb[c], axis=0)
+            board[flat] = np.tile(board_off[c] + np.arange(nb[c]), sel.size) if c > 0 else -1
+            # parents
+            par_abs = a_parent[sel]
+            has_par = par_abs >= 0
+            pa = np.where(has_par, par_abs, 0)
+            par_is_chance = has_par & (a_kind[pa] == KIND_CHANCE)
+            j_par = np.where(par_is_chance[:, None], self.board_parent[c][None, :] if c > 0 else 0, J)
+            pid = a_base[pa][:, None] + j_par * a_m[pa][:, None] + a_k[pa][:, None]
+            pid = np.where(has_par[:, None], pid, -1)
+            parent[flat] = pid.ravel()
+            # action / DFS offset relative to parent
+            j_local = (J - j_par * fan[c]) if c > 0 else np.zeros_like(J)
+            act = np.where(par_is_chance[:, None], j_local, a_action[sel][:, None])
+            action[flat] = act.ravel()
+            rel = a_reloff[sel][:, None] + np.where(par_is_chance[:, None], j_local * size[sel][:, None], 0)
+            dfs_rel[flat] = rel.ravel()
+            # children
+            fc_abs = a_first_child_abs[sel]
+            has_ch = fc_abs >= 0
+            fa = np.where(has_ch, fc_abs, 0)
+            is_ch = a_kind[sel] == KIND_CHANCE
+            nch = np.where(is_ch, fan[min(c + 1, n_cd)], a_nch[sel])
+            fc = a_base[fa][:, None] + J * nch[:, None]
+            first_child[flat] = np.where(has_ch[:, None], fc, -1).ravel()
+            n_children[flat] = np.where(has_ch[:, None], np.broadcast_to(nch[:, None], ids.shape), 0).ravel()
+
+        # absolute DFS index, top-down by level
+        dfs = np.zeros(N, np.int64)
+        for d in range(1, self.n_levels):
+            lo, hi = self.level_start[d], self.level_start[d + 1]
+            dfs[lo:hi] = dfs[parent[lo:hi]] + dfs_rel[lo:hi]
+        # table slots: children of decision nodes, in flat order (so one decision node's rows are contiguous)
+        is_dec_child = np.zeros(N, bool)
+        nz = parent >= 0
+        is_dec_child[nz] = kind[parent[nz]] <= KIND_P1
+        slot = np.full(N, -1, np.int32)
+        slot[is_dec_child] = np.arange(int(is_dec_child.sum()), dtype=np.int32)
+        first_slot = np.full(N, -1, np.int32)
+        dec = (kind <= KIND_P1) & (first_child >= 0)
+        first_slot[dec] = slot[first_child[dec]]
+
+        self.parent, self.first_child, self.n_children = parent, first_child, n_children
+        self.kind, self.acted_last, self.action = kind, acted_last, action
+        self.pot, self.round, self.board, self.abs_id = pot, rnd, board, abs_id
+        self.stack, self.bet = stack, bet
+        self.dfs = dfs
+        self.slot, self.first_slot = slot, first_slot
+        self.n_slots = int(is_dec_child.sum())
+        self.n_nonterm = int(((kind <= KIND_CHANCE) & (first_child >= 0)).sum())
+        self.n_decision = int(dec.sum())
+        self.max_actions = int(n_children[dec].max()) if dec.any() else 0
+
+    # ------------------------------------------------------------------ helpers
+    def board_cards(self):
+        """int8 [n_boards_total, N_TOTAL_BOARD_CARDS] padded with the not-dealt token, global board id order."""
+        nmax = max(self.rules.N_TOTAL_BOARD_CARDS, 1)
+        rows = []
+        for b in self.boards:
+            pad = np.full((b.shape[0], nmax), Poker.CARD_NOT_DEALT_TOKEN_1D, np.int8)
+            pad[:, :b.shape[1]] = b
+            rows.append(pad)
+        return np.concatenate(rows, axis=0)
+
+    def node_board_cards(self):
+        """int8 [N, N_TOTAL_BOARD_CARDS]; not-dealt token where no board."""
+        bc = self.board_cards()
+        out = np.full((self.n_nodes, bc.shape[1]), Poker.CARD_NOT_DEALT_TOKEN_1D, np.int8)
+        m = self.board >= 0
+        # board == -1 means chance depth 0 -> global board 0 (empty)
+        out[m] = bc[self.board[m]]
+        return out
+
+    def dfs_permutation(self):
+        """perm such that array_in_dfs_order = array_in_flat_order[perm]"""
+        perm = np.empty(self.n_nodes, np.int64)
+        perm[self.dfs] = np.arange(self.n_nodes)
+        return perm
