@@ -1,0 +1,114 @@
+/*
+ * pokerrl_b200 — C ABI of the B200-native tabular CFR / public-tree / best-response path.
+ *
+ * Drop-in boundary.  The reference has no native code on this path — its only FFI precedent is the
+ * ctypes convention of PokerRL/_/CppWrapper.py:10-27 (caller allocates every buffer, native code only writes into
+ * them, plain pointers and sizes, no ownership transfer).  This header keeps that convention: every pointer marked
+ * DEVICE is a raw CUDA device pointer owned by the caller (a torch tensor's data_ptr()), every call is asynchronous
+ * on the given CUDA stream, returns 0 on success or a non-zero code with a message in prl_last_error().
+ *
+ * Each entry point cites the reference interface it replaces (file:line under PokerRL/).
+ *
+ * Vector layout: every per-node vector is a row of `ld` floats (ld >= n_range, row h = hand / range index in the
+ * reference's LUT order: one-card games h = 1D card id; two-card games h = LUT_HOLE_CARDS_2_IDX[c1,c2]).  Per-node
+ * arrays are player-major: reach/ev/ev_br = float[2][n_nodes][ld].  Tables (regret, strategy, average) have one row
+ * per child of a decision node ("slot"): float[n_slots][ld].
+ */
+#ifndef POKERRL_B200_H
+#define POKERRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* prl_stream_t; /* cudaStream_t */
+
+/* node kinds (game/_/tree/_/nodes.py:8-62 + ValueFiller.py:34-62) */
+enum {
+    PRL_KIND_P0 = 0,             /* player 0 acts next */
+    PRL_KIND_P1 = 1,             /* player 1 acts next */
+    PRL_KIND_CHANCE = 2,         /* chance acts next ("Ch") */
+    PRL_KIND_FOLD = 3,           /* terminal: acted_last folded */
+    PRL_KIND_SHOWDOWN = 4,       /* terminal: showdown with complete board */
+    PRL_KIND_SHOWDOWN_ALLIN = 5  /* terminal: all-in showdown before the board is complete */
+};
+
+/* algorithms (cfr/VanillaCFR.py, cfr/CFRPlus.py, cfr/LinearCFR.py) */
+enum { PRL_ALGO_VANILLA = 0, PRL_ALGO_CFR_PLUS = 1, PRL_ALGO_LINEAR = 2 };
+
+/* where a player's strategy comes from in a reach / value pass, and in which precision the reference computes
+ * with it */
+enum {
+    PRL_STRAT_F32 = 0,       /* float table `strat`                       (after the player's first update)        */
+    PRL_STRAT_UNIFORM64 = 1, /* 1.0/A in double                            (StrategyFiller.py:61-62, before it)     */
+    PRL_STRAT_AVG_F64 = 2,   /* double table `avg`                         (CFR+ average under numpy>=2)            */
+    PRL_STRAT_AVG_SUM = 3,   /* float table `avg` holding reach-weighted sums, normalised on the fly, double math
+                                                                           (LinearCFR.py:64-71, VanillaCFR.py:65-72) */
+    PRL_STRAT_AVG_F32 = 4    /* float table `avg` used as is, float math   (CFR+ average under numpy<2)             */
+};
+
+/* Depth-sorted public tree in HBM (replaces the object tree of game/_/tree/PublicTree.py:111-293, nodes.py). */
+typedef struct {
+    int32_t n_nodes, n_levels, n_slots;
+    int32_t n_range;    /* RANGE_SIZE */
+    int32_t ld;         /* row stride in elements */
+    int32_t n_hole;     /* hole cards per hand: 1 (Leduc family) or 2 (Hold'em family) */
+    int32_t n_deck;     /* N_CARDS_IN_DECK */
+    int32_t n_suits;    /* N_SUITS (card c = rank * n_suits + suit) */
+    int32_t pair_bonus; /* one-card games: added to the rank of a hand pairing the board (game_rules.py:68-75) */
+    int32_t max_actions;
+    const int64_t* level_start;  /* HOST int64[n_levels+1]: nodes of depth d are [level_start[d], level_start[d+1]) */
+    const int32_t* parent;       /* DEVICE int32[n_nodes], -1 for the root */
+    const int32_t* first_child;  /* DEVICE int32[n_nodes], -1 if none; children are contiguous */
+    const int32_t* n_children;   /* DEVICE int32[n_nodes] */
+    const int32_t* slot;         /* DEVICE int32[n_nodes]: table row of this node as a child of a decision node, else -1 */
+    const int8_t* kind;          /* DEVICE int8[n_nodes] */
+    const int8_t* acted_last;    /* DEVICE int8[n_nodes]: seat that acted last (folder at fold terminals) */
+    const float* pot;            /* DEVICE float[n_nodes]: main pot (chips) */
+    const int32_t* board;        /* DEVICE int32[n_nodes]: one-card games: the board card or -1; two-card games: board id */
+} prl_tree_t;
+
+/* Caller-owned work buffers. */
+typedef struct {
+    float* reach;  /* DEVICE float[2][n_nodes][ld]   node.reach_probs */
+    float* ev;     /* DEVICE float[2][n_nodes][ld]   node.ev */
+    float* ev_br;  /* DEVICE float[2][n_nodes][ld]   node.ev_br (may be NULL when no pass asks for BR) */
+    float* regret; /* DEVICE float[n_slots][ld]      node.data["regret"] */
+    float* strat;  /* DEVICE float[n_slots][ld]      node.strategy */
+    void* avg;     /* DEVICE float|double[n_slots][ld]  node.data["avg_strat"] (CFR+) / ["avg_strat_sum"] */
+} prl_buffers_t;
+
+/* library info */
+int prl_abi_version(void);
+const char* prl_last_error(void);
+
+/* StrategyFiller.update_reach_probs (StrategyFiller.py:118-146) for the seats in player_mask (bit p).
+ * Writes reach[p] of every node from the root down; root = 1/n_range (PublicTree.py:122-124).
+ * strat_mode[p] selects the strategy source of seat p's decision nodes. */
+int prl_reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, const int* strat_mode,
+                   prl_stream_t stream);
+
+/* ValueFiller.compute_cf_values_heads_up (ValueFiller.py:21-101) for the seats in player_mask, bottom-up.
+ * with_br != 0 also fills ev_br.  Terminal values follow ValueFiller.py:103-175. */
+int prl_value_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int with_br,
+                   const int* strat_mode, prl_stream_t stream);
+
+/* Root exploitability (ValueFiller.py:95-101): out_expl = DEVICE float[2], chips. */
+int prl_root_exploitability(const prl_tree_t* tree, const prl_buffers_t* buf, float* out_expl, prl_stream_t stream);
+
+/* One CFR half-iteration for seat p, fused (replaces _CFRBase.py:123-128 for one p):
+ *   bottom-up:  ev[p] of every node; at p's decision nodes regret update (_CFRBase.py:146-185 with the formula of
+ *               algo) and regret matching into `strat` (CFRPlus.py:43-63 / LinearCFR.py:33-51 / VanillaCFR.py:32-52)
+ *   top-down:   reach[p] of every node with the new strategy (StrategyFiller.py:118-146) and the average-strategy
+ *               update of p's nodes (CFRPlus.py:65-87 / LinearCFR.py:53-76 / VanillaCFR.py:54-77)
+ * iter = _iter_counter (0-based); delay = CFR+ averaging delay; avg_f64 = `avg` is double. strat_mode as above
+ * (entry of seat p is what the value pass reads; after the call seat p's strategy is PRL_STRAT_F32). */
+int prl_cfr_half_iteration(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
+                           int avg_f64, const int* strat_mode, prl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POKERRL_B200_H */

@@ -1,0 +1,69 @@
+"""ctypes binding of libpokerrl_b200.so (the C ABI declared in include/pokerrl_b200.h).
+
+There is NO CPU fallback: if the library is missing or a call fails this module raises.  The numpy/C oracle under
+oracle/ is test infrastructure and is never imported from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpokerrl_b200.so")
+
+# enums of include/pokerrl_b200.h
+KIND_P0, KIND_P1, KIND_CHANCE, KIND_FOLD, KIND_SHOWDOWN, KIND_SHOWDOWN_ALLIN = range(6)
+ALGO_VANILLA, ALGO_CFR_PLUS, ALGO_LINEAR = 0, 1, 2
+STRAT_F32, STRAT_UNIFORM64, STRAT_AVG_F64, STRAT_AVG_SUM, STRAT_AVG_F32 = range(5)
+
+
+class PrlTree(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int32), ("n_levels", C.c_int32), ("n_slots", C.c_int32), ("n_range", C.c_int32),
+        ("ld", C.c_int32), ("n_hole", C.c_int32), ("n_deck", C.c_int32), ("n_suits", C.c_int32),
+        ("pair_bonus", C.c_int32), ("max_actions", C.c_int32),
+        ("level_start", C.c_void_p),
+        ("parent", C.c_void_p), ("first_child", C.c_void_p), ("n_children", C.c_void_p), ("slot", C.c_void_p),
+        ("kind", C.c_void_p), ("acted_last", C.c_void_p), ("pot", C.c_void_p), ("board", C.c_void_p),
+    ]
+
+
+class PrlBuffers(C.Structure):
+    _fields_ = [("reach", C.c_void_p), ("ev", C.c_void_p), ("ev_br", C.c_void_p), ("regret", C.c_void_p),
+                ("strat", C.c_void_p), ("avg", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library on first use; raises if it has not been built (python -m pokerrl_b200.csrc.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "pokerrl_b200: CUDA library %s is missing. Build it with `python -m pokerrl_b200.csrc.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.prl_abi_version.restype = C.c_int
+    L.prl_last_error.restype = C.c_char_p
+    tp, bp, ip = C.POINTER(PrlTree), C.POINTER(PrlBuffers), C.POINTER(C.c_int)
+    L.prl_reach_pass.argtypes = [tp, bp, C.c_int, ip, C.c_void_p]
+    L.prl_value_pass.argtypes = [tp, bp, C.c_int, C.c_int, ip, C.c_void_p]
+    L.prl_root_exploitability.argtypes = [tp, bp, C.c_void_p, C.c_void_p]
+    L.prl_cfr_half_iteration.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_void_p]
+    for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration"):
+        getattr(L, f).restype = C.c_int
+    _lib = L
+    return L
+
+
+def call(name, *args):
+    """Calls an entry point and raises RuntimeError(prl_last_error()) on a non-zero status."""
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, L.prl_last_error().decode()))
+
+
+def modes(m0, m1):
+    return (C.c_int * 2)(m0, m1)

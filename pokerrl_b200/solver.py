@@ -1,0 +1,184 @@
+"""Device-resident public tree + tabular CFR engine (host side: PyTorch tensors as buffers, ctypes into CUDA).
+
+This is the engine behind the reference-shaped façades in `pokerrl_b200.cfr` / `pokerrl_b200.game.PublicTree` /
+`pokerrl_b200.eval.br`.  All arithmetic happens in libpokerrl_b200.so; this file only owns buffers and the
+iteration schedule of `PokerRL/cfr/_CFRBase.py:110-134`.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from pokerrl_b200 import _native as nat
+
+ALGOS = {"VanillaCFR": nat.ALGO_VANILLA, "CFRPlus": nat.ALGO_CFR_PLUS, "LinearCFR": nat.ALGO_LINEAR}
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("pokerrl_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+    return torch.device(device if device is not None else "cuda:0")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceTree:
+    """FlatTree uploaded to HBM + the prl_tree_t descriptor handed to the C ABI."""
+
+    def __init__(self, ft, device=None):
+        self.ft = ft
+        self.device = _require_cuda(device)
+        rules = ft.rules
+        self.R = ft.R
+        self.ld = ft.R
+        dev = self.device
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(dev)
+
+        board = ft.board.copy().astype(np.int32)
+        if rules.N_HOLE_CARDS == 1:
+            # one-card games: kernels take the board card itself (-1 = none)
+            bc = ft.node_board_cards()[:, 0].astype(np.int32)
+            board = np.where(bc >= 0, bc, -1).astype(np.int32)
+        self.t_parent = up(ft.parent, np.int32)
+        self.t_first_child = up(ft.first_child, np.int32)
+        self.t_n_children = up(ft.n_children, np.int32)
+        self.t_slot = up(ft.slot, np.int32)
+        self.t_kind = up(ft.kind, np.int8)
+        self.t_acted_last = up(ft.acted_last, np.int8)
+        self.t_pot = up(ft.pot, np.float32)
+        self.t_board = up(board, np.int32)
+        self._level_start = np.ascontiguousarray(ft.level_start, dtype=np.int64)
+        d = nat.PrlTree()
+        d.n_nodes, d.n_levels, d.n_slots = ft.n_nodes, ft.n_levels, ft.n_slots
+        d.n_range, d.ld, d.n_hole = self.R, self.ld, rules.N_HOLE_CARDS
+        d.n_deck, d.n_suits = rules.N_CARDS_IN_DECK, rules.N_SUITS
+        d.pair_bonus = rules.PAIR_BONUS or 0
+        d.max_actions = ft.max_actions
+        d.level_start = self._level_start.ctypes.data
+        d.parent, d.first_child = self.t_parent.data_ptr(), self.t_first_child.data_ptr()
+        d.n_children, d.slot = self.t_n_children.data_ptr(), self.t_slot.data_ptr()
+        d.kind, d.acted_last = self.t_kind.data_ptr(), self.t_acted_last.data_ptr()
+        d.pot, d.board = self.t_pot.data_ptr(), self.t_board.data_ptr()
+        self.desc = d
+
+    @property
+    def n_nodes(self):
+        return self.ft.n_nodes
+
+    @property
+    def n_slots(self):
+        return self.ft.n_slots
+
+
+class TreeBuffers:
+    """reach / ev / ev_br node vectors and regret / strategy / average tables (torch tensors in HBM)."""
+
+    def __init__(self, dtree, with_tables=True, avg_dtype=torch.float32, share=None):
+        dev, N, S, ld = dtree.device, dtree.n_nodes, dtree.n_slots, dtree.ld
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)  # noqa: E731
+        self.reach = z(2, N, ld)
+        if share is None:
+            self.ev, self.ev_br = z(2, N, ld), z(2, N, ld)
+            self.regret = z(S, ld) if with_tables else None
+            self.strat = z(S, ld) if with_tables else None
+            self.avg = z(S, ld, dtype=avg_dtype) if with_tables else None
+        else:  # evaluation view: own reach, everything else shared with the training buffers
+            self.ev, self.ev_br = share.ev, share.ev_br
+            self.regret, self.strat, self.avg = share.regret, share.strat, share.avg
+        d = nat.PrlBuffers()
+        d.reach, d.ev, d.ev_br = self.reach.data_ptr(), self.ev.data_ptr(), self.ev_br.data_ptr()
+        d.regret = self.regret.data_ptr() if self.regret is not None else None
+        d.strat = self.strat.data_ptr() if self.strat is not None else None
+        d.avg = self.avg.data_ptr() if self.avg is not None else None
+        self.desc = d
+
+
+class TreeOps:
+    """Thin wrappers over the C ABI passes for one (tree, buffers) pair."""
+
+    def __init__(self, dtree, bufs):
+        self.dtree, self.bufs = dtree, bufs
+        self._expl = torch.zeros(2, dtype=torch.float32, device=dtree.device)
+
+    def reach_pass(self, modes, player_mask=3):
+        nat.call("prl_reach_pass", C.byref(self.dtree.desc), C.byref(self.bufs.desc), player_mask,
+                 nat.modes(*modes), _stream())
+
+    def value_pass(self, modes, player_mask=3, with_br=True):
+        nat.call("prl_value_pass", C.byref(self.dtree.desc), C.byref(self.bufs.desc), player_mask, int(with_br),
+                 nat.modes(*modes), _stream())
+
+    def root_exploitability(self):
+        """float32[2] chips (device->host read)."""
+        nat.call("prl_root_exploitability", C.byref(self.dtree.desc), C.byref(self.bufs.desc),
+                 C.c_void_p(self._expl.data_ptr()), _stream())
+        return self._expl.cpu().numpy()
+
+
+class CFRSolver:
+    """Iteration schedule of `_CFRBase` (reset :110-120, iteration :122-134) on the GPU.
+
+    One `iteration()` = for p in (0, 1): fused half-iteration (value pass for p with regret update and regret
+    matching, then reach pass for p with the average-strategy update).  Exploitability of the current / average
+    strategy is a separate, optional evaluation (the reference does both every iteration).
+    """
+
+    def __init__(self, ft, algo="CFRPlus", delay=0, device=None, avg_f64=False):
+        self.algo_name = algo
+        self.algo = ALGOS[algo]
+        self.delay = int(delay) if algo == "CFRPlus" else 0
+        self.avg_f64 = bool(avg_f64) and algo == "CFRPlus"
+        self.dtree = DeviceTree(ft, device)
+        self.bufs = TreeBuffers(self.dtree, avg_dtype=torch.float64 if self.avg_f64 else torch.float32)
+        self.ops = TreeOps(self.dtree, self.bufs)
+        self._eval_bufs = None
+        self.ev_normalizer = ft.game_cls.EV_NORMALIZER
+        self.reset()
+
+    def reset(self):
+        self.iter_counter = 0
+        for t in (self.bufs.regret, self.bufs.strat, self.bufs.avg):
+            t.zero_()
+        self.modes = [nat.STRAT_UNIFORM64, nat.STRAT_UNIFORM64]  # StrategyFiller.py:61-62
+        self.ops.reach_pass(self.modes)
+
+    def iteration(self, n=1):
+        tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
+        for _ in range(n):
+            for p in (0, 1):
+                nat.call("prl_cfr_half_iteration", tree, buf, self.algo, p, self.iter_counter, self.delay,
+                         int(self.avg_f64), nat.modes(*self.modes), _stream())
+                self.modes[p] = nat.STRAT_F32
+            self.iter_counter += 1
+
+    # ---- evaluation (_CFRBase._log_curr_strat_expl :198-216, _evaluate_avg_strats :218-262)
+    def _metric(self, expl):
+        e = [float(expl[p]) * self.ev_normalizer for p in range(2)]
+        return sum(e) / 2
+
+    def exploitability_current(self):
+        self.ops.value_pass(self.modes, 3, True)
+        return self._metric(self.ops.root_exploitability())
+
+    def average_modes(self):
+        if self.algo != nat.ALGO_CFR_PLUS:
+            return [nat.STRAT_AVG_SUM, nat.STRAT_AVG_SUM]
+        if self.iter_counter <= self.delay:
+            raise RuntimeError("CFR+ has no average strategy before iteration delay+1 (CFRPlus.py:33-35)")
+        if self.iter_counter == self.delay + 1:
+            return [nat.STRAT_F32, nat.STRAT_F32]  # avg == copy of the current strategy (CFRPlus.py:83-84)
+        m = nat.STRAT_AVG_F64 if self.avg_f64 else nat.STRAT_AVG_F32
+        return [m, m]
+
+    def exploitability_average(self):
+        if self._eval_bufs is None:
+            self._eval_bufs = TreeBuffers(self.dtree, share=self.bufs)
+            self._eval_ops = TreeOps(self.dtree, self._eval_bufs)
+        m = self.average_modes()
+        self._eval_ops.reach_pass(m)
+        self._eval_ops.value_pass(m, 3, True)
+        return self._metric(self._eval_ops.root_exploitability())

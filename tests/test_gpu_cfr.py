@@ -1,0 +1,107 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the reference's golden fixtures.
+
+Bar (integer work: bit-exact; float work: the tolerance BASELINE.json states, 1e-6 relative): in practice every
+float32 quantity of the one-card games is reproduced BIT-FOR-BIT, because the kernels evaluate in the reference's
+dtypes and operation order — the tests therefore assert exact equality and would catch any
+reordering.
+"""
+import numpy as np
+import pytest
+import torch
+
+from common import golden, make_flat_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def _node_vec(ft, t):  # torch [2, N, ld] -> numpy [N, 2, R] in DFS order
+    a = t.cpu().numpy()[:, :, :ft.R].transpose(1, 0, 2)
+    return a[ft.dfs_permutation()]
+
+
+def _table(ft, t):  # torch [n_slots, ld] -> numpy [N, R] (NaN where the node has no slot) in DFS order
+    a = t.cpu().numpy()[:, :ft.R].astype(np.float64)
+    out = np.full((ft.n_nodes, ft.R), np.nan)
+    m = ft.slot >= 0
+    out[m] = a[ft.slot[m]]
+    return out[ft.dfs_permutation()]
+
+
+@pytest.mark.parametrize("name", ["StandardLeduc", "NLLeduc_POT", "NLLeduc_B2"])
+def test_uniform_and_random_profile_bit_exact(name):
+    from pokerrl_b200 import _native as nat
+    from pokerrl_b200.solver import CFRSolver
+    ft = make_flat_tree(name)
+    g = golden("values_%s.npz" % name)
+    s = CFRSolver(ft, "CFRPlus", avg_f64=True)
+    s.exploitability_current()
+    for k, t in (("reach", s.bufs.reach), ("ev", s.bufs.ev), ("ev_br", s.bufs.ev_br)):
+        assert np.array_equal(_node_vec(ft, t), g["uniform_" + k]), k
+    assert np.array_equal(s.ops.root_exploitability(), g["uniform_root_exploitability"])
+    # seeded random float64 profile of the reference -> double table, evaluated like an average strategy
+    strat = g["random_strat"]  # [N, R] DFS order
+    tab = np.zeros((ft.n_slots, ft.R))
+    m = ft.slot >= 0
+    tab[ft.slot[m]] = strat[ft.dfs[m]]
+    s.bufs.avg.copy_(torch.from_numpy(tab))
+    modes = [nat.STRAT_AVG_F64, nat.STRAT_AVG_F64]
+    s.ops.reach_pass(modes)
+    s.ops.value_pass(modes, 3, True)
+    for k, t in (("reach", s.bufs.reach), ("ev", s.bufs.ev), ("ev_br", s.bufs.ev_br)):
+        assert np.array_equal(_node_vec(ft, t), g["random_" + k]), k
+    assert np.array_equal(s.ops.root_exploitability(), g["random_root_exploitability"])
+
+
+def test_b3_uniform_root():
+    from pokerrl_b200.solver import CFRSolver
+    ft = make_flat_tree("NLLeduc_B3")
+    g = golden("values_NLLeduc_B3.npz")
+    s = CFRSolver(ft, "CFRPlus")
+    s.exploitability_current()
+    assert np.array_equal(s.bufs.ev[:, 0, :ft.R].cpu().numpy(), g["uniform_root_ev"])
+    assert np.array_equal(s.bufs.ev_br[:, 0, :ft.R].cpu().numpy(), g["uniform_root_ev_br"])
+    assert np.array_equal(s.ops.root_exploitability(), g["uniform_root_exploitability"])
+
+
+@pytest.mark.parametrize("algo,name", [
+    ("CFRPlus", "NLLeduc_POT"), ("CFRPlus", "StandardLeduc"),
+    ("LinearCFR", "NLLeduc_POT"), ("LinearCFR", "StandardLeduc"),
+    ("VanillaCFR", "NLLeduc_POT"), ("VanillaCFR", "StandardLeduc"),
+])
+def test_cfr_trajectory_bit_exact(algo, name):
+    from pokerrl_b200.solver import CFRSolver
+    ft = make_flat_tree(name)
+    g = golden("cfr_%s_%s.npz" % (algo, name))
+    s = CFRSolver(ft, algo, avg_f64=True)
+    n_iters = 40 if algo != "CFRPlus" else (150 if name == "NLLeduc_POT" else 60)
+    curr, avg = [(0, s.exploitability_current())], []
+    snaps = (1, 2, 3, 4, 5, 10, 11, 30, 31)
+    for t in range(1, n_iters + 1):
+        s.iteration()
+        curr.append((t, s.exploitability_current()))
+        if t in snaps:
+            assert np.array_equal(_table(ft, s.bufs.regret), g["it%d_regret" % t], equal_nan=True), t
+            assert np.array_equal(_table(ft, s.bufs.strat), g["it%d_strat" % t], equal_nan=True), t
+            for k, buf in (("reach", s.bufs.reach), ("ev", s.bufs.ev), ("ev_br", s.bufs.ev_br)):
+                assert np.array_equal(_node_vec(ft, buf), g["it%d_%s" % (t, k)]), (t, k)
+            if algo == "CFRPlus":
+                assert np.array_equal(_table(ft, s.bufs.avg), g["it%d_avg" % t], equal_nan=True), t
+            else:
+                assert np.array_equal(_table(ft, s.bufs.avg), g["it%d_avg_sum" % t], equal_nan=True), t
+        avg.append((t, s.exploitability_average()))
+    assert np.array_equal(np.array(curr), g["curr_series"]), "current-strategy exploitability series"
+    assert np.array_equal(np.array(avg), g["avg_series"]), "average-strategy exploitability series"
+
+
+def test_cfr_plus_float32_average_within_tolerance():
+    """The float32 average table (reference semantics under numpy<2, and the fast default) stays within the
+    1e-6 relative tolerance of the float64-average reference run."""
+    from pokerrl_b200.solver import CFRSolver
+    ft = make_flat_tree("NLLeduc_POT")
+    g = golden("cfr_CFRPlus_NLLeduc_POT.npz")
+    s = CFRSolver(ft, "CFRPlus", avg_f64=False)
+    for t in range(1, 61):
+        s.iteration()
+        a = s.exploitability_average()
+        ref = g["avg_series"][t - 1, 1]
+        assert abs(a - ref) <= 1e-6 * abs(ref), (t, a, ref)
