@@ -83,6 +83,8 @@ typedef struct {
 /* library info */
 int prl_abi_version(void);
 const char* prl_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process */
+unsigned long long prl_launch_count(void);
 
 /* StrategyFiller.update_reach_probs (StrategyFiller.py:118-146) for the seats in player_mask (bit p).
  * Writes reach[p] of every node from the root down; root = 1/n_range (PublicTree.py:122-124).
@@ -107,6 +109,11 @@ int prl_root_exploitability(const prl_tree_t* tree, const prl_buffers_t* buf, fl
  * (entry of seat p is what the value pass reads; after the call seat p's strategy is PRL_STRAT_F32). */
 int prl_cfr_half_iteration(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
                            int avg_f64, const int* strat_mode, prl_stream_t stream);
+
+/* The two sweeps of prl_cfr_half_iteration separately (which: bit 0 = bottom-up value/regret sweep, bit 1 = top-down
+ * reach/average sweep); prl_cfr_half_iteration == which 3.  Used to time the sweeps individually. */
+int prl_cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay, int avg_f64,
+                  const int* strat_mode, int which, prl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -51,7 +51,9 @@ def lib():
     L.prl_value_pass.argtypes = [tp, bp, C.c_int, C.c_int, ip, C.c_void_p]
     L.prl_root_exploitability.argtypes = [tp, bp, C.c_void_p, C.c_void_p]
     L.prl_cfr_half_iteration.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_void_p]
-    for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration"):
+    L.prl_cfr_sweep.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_void_p]
+    L.prl_launch_count.restype = C.c_ulonglong
+    for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration", "prl_cfr_sweep"):
         getattr(L, f).restype = C.c_int
     _lib = L
     return L

@@ -266,6 +266,8 @@ __global__ void root_exploitability_kernel(prl_tree_t T, prl_buffers_t B, float*
 
 constexpr int kThreads = 256;
 
+#define PRL_LAUNCH(kernel, grid, stream, ...) do { kernel<<<(grid), kThreads, 0, (stream)>>>(__VA_ARGS__); prl::count_launch(); } while (0)
+
 inline unsigned grid_for(long long n_threads) { return (unsigned)((n_threads + kThreads - 1) / kThreads); }
 
 int check_tree(const prl_tree_t* t) {
@@ -285,7 +287,7 @@ extern "C" int prl_reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, 
         c.hi = (int)tree->level_start[d + 1];
         long long nt = (long long)(c.hi - c.lo) * tree->n_range;
         if (nt == 0) continue;
-        reach_level_kernel<false><<<grid_for(nt), kThreads, 0, s>>>(c);
+        PRL_LAUNCH(reach_level_kernel<false>, grid_for(nt), s, c);
     }
     return prl::check(cudaGetLastError(), "prl_reach_pass");
 }
@@ -301,8 +303,8 @@ extern "C" int prl_value_pass(const prl_tree_t* tree, const prl_buffers_t* buf, 
         c.hi = (int)tree->level_start[d + 1];
         long long nt = (long long)(c.hi - c.lo) * tree->n_range;
         if (nt == 0) continue;
-        if (with_br) value_level_kernel<true, false><<<grid_for(nt), kThreads, 0, s>>>(c);
-        else value_level_kernel<false, false><<<grid_for(nt), kThreads, 0, s>>>(c);
+        if (with_br) PRL_LAUNCH((value_level_kernel<true, false>), grid_for(nt), s, c);
+        else PRL_LAUNCH((value_level_kernel<false, false>), grid_for(nt), s, c);
     }
     return prl::check(cudaGetLastError(), "prl_value_pass");
 }
@@ -311,30 +313,40 @@ extern "C" int prl_root_exploitability(const prl_tree_t* tree, const prl_buffers
                                        prl_stream_t stream) {
     if (!buf->ev_br) return prl::fail("prl_root_exploitability needs ev_br");
     root_exploitability_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*tree, *buf, out_expl);
+    prl::count_launch();
     return prl::check(cudaGetLastError(), "prl_root_exploitability");
+}
+
+extern "C" int prl_cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
+                             int avg_f64, const int* strat_mode, int which, prl_stream_t stream) {
+    if (int e = check_tree(tree)) return e;
+    if (p < 0 || p > 1 || algo < 0 || algo > 2) return prl::fail("prl_cfr_sweep: bad p / algo");
+    if (algo != PRL_ALGO_CFR_PLUS && avg_f64) return prl::fail("avg_f64 only applies to CFR+");
+    Ctx c{*tree, *buf, 0, 0, 1 << p, {strat_mode[0], strat_mode[1]}, algo, p, iter, delay, avg_f64};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (which & 1) {
+        for (int d = tree->n_levels - 1; d >= 0; --d) {
+            c.lo = (int)tree->level_start[d];
+            c.hi = (int)tree->level_start[d + 1];
+            long long nt = (long long)(c.hi - c.lo) * tree->n_range;
+            if (nt == 0) continue;
+            PRL_LAUNCH((value_level_kernel<false, true>), grid_for(nt), s, c);
+        }
+    }
+    if (which & 2) {
+        c.mode[p] = PRL_STRAT_F32;  // p's strategy now lives in the float table
+        for (int d = 0; d < tree->n_levels; ++d) {
+            c.lo = (int)tree->level_start[d];
+            c.hi = (int)tree->level_start[d + 1];
+            long long nt = (long long)(c.hi - c.lo) * tree->n_range;
+            if (nt == 0) continue;
+            PRL_LAUNCH(reach_level_kernel<true>, grid_for(nt), s, c);
+        }
+    }
+    return prl::check(cudaGetLastError(), "prl_cfr_sweep");
 }
 
 extern "C" int prl_cfr_half_iteration(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter,
                                       int delay, int avg_f64, const int* strat_mode, prl_stream_t stream) {
-    if (int e = check_tree(tree)) return e;
-    if (p < 0 || p > 1 || algo < 0 || algo > 2) return prl::fail("prl_cfr_half_iteration: bad p / algo");
-    if (algo != PRL_ALGO_CFR_PLUS && avg_f64) return prl::fail("avg_f64 only applies to CFR+");
-    Ctx c{*tree, *buf, 0, 0, 1 << p, {strat_mode[0], strat_mode[1]}, algo, p, iter, delay, avg_f64};
-    cudaStream_t s = (cudaStream_t)stream;
-    for (int d = tree->n_levels - 1; d >= 0; --d) {
-        c.lo = (int)tree->level_start[d];
-        c.hi = (int)tree->level_start[d + 1];
-        long long nt = (long long)(c.hi - c.lo) * tree->n_range;
-        if (nt == 0) continue;
-        value_level_kernel<false, true><<<grid_for(nt), kThreads, 0, s>>>(c);
-    }
-    c.mode[p] = PRL_STRAT_F32;  // p's strategy now lives in the float table
-    for (int d = 0; d < tree->n_levels; ++d) {
-        c.lo = (int)tree->level_start[d];
-        c.hi = (int)tree->level_start[d + 1];
-        long long nt = (long long)(c.hi - c.lo) * tree->n_range;
-        if (nt == 0) continue;
-        reach_level_kernel<true><<<grid_for(nt), kThreads, 0, s>>>(c);
-    }
-    return prl::check(cudaGetLastError(), "prl_cfr_half_iteration");
+    return prl_cfr_sweep(tree, buf, algo, p, iter, delay, avg_f64, strat_mode, 3, stream);
 }

@@ -7,6 +7,7 @@
 
 namespace {
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 }
 
 namespace prl {
@@ -20,7 +21,9 @@ int check(cudaError_t e, const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return (int)e;
 }
+void count_launch() { ++g_launches; }
 }  // namespace prl
 
 extern "C" int prl_abi_version(void) { return 1; }
 extern "C" const char* prl_last_error(void) { return g_err; }
+extern "C" unsigned long long prl_launch_count(void) { return g_launches; }

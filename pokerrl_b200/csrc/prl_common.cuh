@@ -7,4 +7,6 @@ namespace prl {
 int fail(const char* msg);
 // cudaSuccess -> 0; otherwise records "<where>: <cuda error string>" and returns the CUDA error code.
 int check(cudaError_t e, const char* where);
+// counts kernel launches issued by this library (prl_launch_count())
+void count_launch();
 }  // namespace prl
