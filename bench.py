@@ -88,7 +88,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -137,8 +137,8 @@ def run_cpu(ft, n_iters, eval_every, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="leduc_b5", choices=list(WORKLOADS))
     ap.add_argument("--eval-every", type=int, default=20)
@@ -161,7 +161,8 @@ def main():
         g, ft = make_tree(a.workload, 20000)
         st = tree_stats(ft)
         ncpu = os.cpu_count() or 1
-        sec, threads = run_cpu(ft, K, a.eval_every, ncpu)
+        K = min(K, 200)
+        sec, threads = run_cpu(ft, K, a.eval_every, min(ncpu, 16))
         cfg.update(tree=st)
         v = 1.0 / sec
         print(json.dumps({
@@ -204,6 +205,17 @@ def main():
             return s.exploitability_current(), s.exploitability_average()
         return None
 
+    def steps(i0, n):
+        """n steps starting at step index i0; iterations between two evaluations share one persistent launch"""
+        out, i = [], i0
+        while i < i0 + n:
+            m = min(a.eval_every - (i % a.eval_every), i0 + n - i)
+            s.iteration(m)
+            i += m
+            if i % a.eval_every == 0:
+                out.append((i, s.exploitability_current(), s.exploitability_average()))
+        return out
+
     for i in range(W):
         step(i)
     s.reset()  # timed run starts from iteration 0 so that the exploitability trace is the reference's
@@ -217,15 +229,18 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.5)  # let nvidia-smi start sampling; the GPU is kept busy by an untimed step stream meanwhile
+        for i in range(W):
+            s.iteration(1)
+        s.reset()
+        torch.cuda.synchronize()
     launches0 = nat.lib().prl_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     trace = []
     wall0 = time.perf_counter()
     ev0.record()
-    for i in range(K):
-        r = step(i)
-        if r is not None:
-            trace.append((i + 1, r[0], r[1]))
+    trace = steps(0, K)
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
@@ -270,38 +285,35 @@ def main():
     n_evals = K // a.eval_every
     d2h_per_step = 2 * 8 * n_evals / K  # two float32[2] exploitability read-backs per evaluation
 
-    # --- roofline of the dominant kernel (value/regret sweep), timed live with events, sweep by sweep
+    # --- roofline of the dominant kernel: the persistent cooperative kernel that runs whole CFR+ iterations
+    # (cfr_iterations_kernel, one launch per `eval_every` iterations), timed live with CUDA events on its stream
     s = cfr.solvers[0]
-    tree_p, buf_p = C.byref(s.dtree.desc), C.byref(s.bufs.desc)
-    val_ms, reach_ms = [], []
-    for rep in range(10):
-        for p in (0, 1):
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            evs[0].record()
-            nat.call("prl_cfr_sweep", tree_p, buf_p, s.algo, p, s.iter_counter, 0, 0, nat.modes(*s.modes), 1, _stream())
-            evs[1].record()
-            nat.call("prl_cfr_sweep", tree_p, buf_p, s.algo, p, s.iter_counter, 0, 0, nat.modes(*s.modes), 2, _stream())
-            evs[2].record()
-            torch.cuda.synchronize()
-            if rep >= 2:
-                val_ms.append(evs[0].elapsed_time(evs[1]))
-                reach_ms.append(evs[1].elapsed_time(evs[2]))
-        s.iter_counter += 1
+    it_ms = []
+    for rep in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s.iteration(a.eval_every)
+        e1.record()
+        torch.cuda.synchronize()
+        if rep >= 2:
+            it_ms.append(e0.elapsed_time(e1))
     vb, rb = algorithmic_bytes(st)
+    bytes_per_launch = a.eval_every * 2 * (vb + rb)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    v_ms = statistics.mean(val_ms)
-    achieved = vb / (v_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "value_level_kernel<false,true> (one bottom-up value/regret sweep = %d launches)" % st["levels"],
+    l_ms = statistics.mean(it_ms)
+    achieved = bytes_per_launch / (l_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "cfr_iterations_kernel<6,2> (persistent cooperative kernel: %d CFR+ iterations = "
+                "%d level steps with grid barriers per launch)" % (a.eval_every, a.eval_every * 2 * (2 * st["levels"] - 1)),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_sweep": vb, "sweep_ms": v_ms, "traffic": None,
-                "reach_sweep": {"algorithmic_bytes": rb, "sweep_ms": statistics.mean(reach_ms),
-                                "achieved": rb / (statistics.mean(reach_ms) * 1e-3) / 1e9}}
+                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": l_ms,
+                "algorithmic_bytes_per_iteration": 2 * (vb + rb), "traffic": None,
+                "note": "latency/occupancy-bound, not HBM-bound: R = 6 rows, 27 dependent level steps per seat"}
 
     if rank != 0:
         if world > 1:
@@ -331,7 +343,7 @@ def main():
         n = max(2, min(K, int(15.0 / max(per_iter_guess, 1e-4))))
         n = (n // a.eval_every) * a.eval_every or n
         _, ft0 = (g, ft)
-        sec, threads = run_cpu(ft0, n, a.eval_every, ncpu)
+        sec, threads = run_cpu(ft0, n, a.eval_every, min(ncpu, 16))
         out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "iterations/s", "cores": threads, "kind": "port",
                                "sample": "%d full CFR+ iterations (same tree, same BR cadence) by oracle/cfr_oracle.c "
                                          "with OpenMP; the reference's own Python path is ~400x slower per node "

@@ -68,6 +68,13 @@ typedef struct {
     const int8_t* acted_last;    /* DEVICE int8[n_nodes]: seat that acted last (folder at fold terminals) */
     const float* pot;            /* DEVICE float[n_nodes]: main pot (chips) */
     const int32_t* board;        /* DEVICE int32[n_nodes]: one-card games: the board card or -1; two-card games: board id */
+    const int32_t* order;        /* DEVICE int32[n_nodes]: per level, the node ids of that level sorted by (kind,
+                                    n_children) with terminals last - thread t of a level works on node order[t], so a
+                                    warp holds nodes of one kind (no divergence); data layout is unaffected */
+    const int64_t* level_nonterm; /* HOST int64[n_levels]: number of non-terminal nodes of each level */
+    const void* meta;            /* DEVICE 16-byte record per node, filled by prl_pack_node_meta() from the arrays above:
+                                    {first_child, first_slot, pot, kind | acted_last | board | n_children}; the sweeps
+                                    read node structure only through it (one 128-bit load per node) */
 } prl_tree_t;
 
 /* Caller-owned work buffers. */
@@ -85,6 +92,10 @@ int prl_abi_version(void);
 const char* prl_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process */
 unsigned long long prl_launch_count(void);
+
+/* Packs the per-node structure arrays of `tree` into out_meta = DEVICE int4[n_nodes] (then set tree->meta = out_meta).
+ * Call once after uploading a tree (the analogue of PublicTree.build_tree finishing, PublicTree.py:111-126). */
+int prl_pack_node_meta(const prl_tree_t* tree, void* out_meta, prl_stream_t stream);
 
 /* StrategyFiller.update_reach_probs (StrategyFiller.py:118-146) for the seats in player_mask (bit p).
  * Writes reach[p] of every node from the root down; root = 1/n_range (PublicTree.py:122-124).
@@ -109,6 +120,23 @@ int prl_root_exploitability(const prl_tree_t* tree, const prl_buffers_t* buf, fl
  * (entry of seat p is what the value pass reads; after the call seat p's strategy is PRL_STRAT_F32). */
 int prl_cfr_half_iteration(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
                            int avg_f64, const int* strat_mode, prl_stream_t stream);
+
+/* n_iters full CFR iterations (_CFRBase.iteration :122-128 without the logging passes) in ONE persistent cooperative
+ * kernel launch: for each iteration, for p in (0, 1): value/regret sweep then reach/average sweep, grid barrier
+ * between tree levels.  iter0 = _iter_counter of the first iteration; strat_mode = sources at entry (seat p switches
+ * to PRL_STRAT_F32 after its first update, exactly like a sequence of prl_cfr_half_iteration calls). */
+int prl_cfr_iterations(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int iter0, int n_iters, int delay,
+                       int avg_f64, const int* strat_mode, prl_stream_t stream);
+
+/* Exploitability evaluation in one persistent launch (_CFRBase._log_curr_strat_expl :198-216 / _evaluate_avg_strats
+ * :218-262; eval/br/LocalBRMaster.py:67-80): optional reach pass for both seats (do_reach), value pass with best
+ * response for both seats, root exploitability -> out_expl = DEVICE float[2] (chips). */
+int prl_evaluate(const prl_tree_t* tree, const prl_buffers_t* buf, const int* strat_mode, int do_reach, float* out_expl,
+                 prl_stream_t stream);
+
+/* Profiling aid: if set to a DEVICE uint64 buffer (>= 1 + 4*n_levels*n_iters entries), prl_cfr_iterations records
+ * %globaltimer (ns) at entry and after every grid barrier; NULL (default) disables it. */
+void prl_debug_set_timeline(void* device_u64_buffer);
 
 /* The two sweeps of prl_cfr_half_iteration separately (which: bit 0 = bottom-up value/regret sweep, bit 1 = top-down
  * reach/average sweep); prl_cfr_half_iteration == which 3.  Used to time the sweeps individually. */

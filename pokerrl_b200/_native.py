@@ -23,6 +23,7 @@ class PrlTree(C.Structure):
         ("level_start", C.c_void_p),
         ("parent", C.c_void_p), ("first_child", C.c_void_p), ("n_children", C.c_void_p), ("slot", C.c_void_p),
         ("kind", C.c_void_p), ("acted_last", C.c_void_p), ("pot", C.c_void_p), ("board", C.c_void_p),
+        ("order", C.c_void_p), ("level_nonterm", C.c_void_p), ("meta", C.c_void_p),
     ]
 
 
@@ -53,7 +54,11 @@ def lib():
     L.prl_cfr_half_iteration.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_void_p]
     L.prl_cfr_sweep.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_void_p]
     L.prl_launch_count.restype = C.c_ulonglong
-    for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration", "prl_cfr_sweep"):
+    L.prl_cfr_iterations.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_void_p]
+    L.prl_evaluate.argtypes = [tp, bp, ip, C.c_int, C.c_void_p, C.c_void_p]
+    L.prl_pack_node_meta.argtypes = [tp, C.c_void_p, C.c_void_p]
+    for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration", "prl_cfr_sweep", "prl_pack_node_meta", "prl_cfr_iterations",
+              "prl_evaluate"):
         getattr(L, f).restype = C.c_int
     _lib = L
     return L

@@ -1,12 +1,18 @@
-// Level-synchronous public-tree sweeps for tabular CFR / best response (sm_100a).
+// Level-synchronous public-tree sweeps for tabular CFR / best response, one-hole-card games (sm_100a).
 //
-// One thread per (node, hand).  Nodes of one depth are contiguous, the children of a node are contiguous and the
-// children groups of adjacent nodes are adjacent, so a warp reads / writes contiguous runs of rows.  These sweeps are
-// HBM/L2-bound vector work (no GEMM shape anywhere): the design rules that matter are coalescing and launch count.
+// Mapping: ONE LANE PER (NODE, HAND); a warp holds 32 / R whole nodes (5 for Leduc's R = 6, 1 for BigLeduc's R = 24),
+// taken from a per-level work list sorted by node kind (no divergence).  Nodes of one depth are contiguous, children of
+// a node are contiguous and children groups of adjacent nodes are adjacent, so a warp reads / writes contiguous runs of
+// rows.  All per-node structure comes from ONE 16-byte record (`prl_tree_t.meta`, LDG.128) so that the dependent chain
+// of a lane is: work-list entry -> record -> {children / table elements, requested together} -> stores; rows of a node
+// are exchanged between its lanes with group-masked warp shuffles.
+//
+// These sweeps are HBM/L2-bound vector work (no GEMM shape anywhere): what matters is coalescing, memory-level
+// parallelism and launch count - not tensor cores.
 //
 // Arithmetic contract: every expression is evaluated in the reference's dtype and operation order
-// (see oracle/cfr_numpy.py, which is pinned bit-for-bit against the reference).  This translation unit is compiled
-// with -fmad=false so that no multiply-add is contracted; the reference (numpy) never fuses.
+// (oracle/cfr_numpy.py and oracle/cfr_oracle.c are pinned bit-for-bit against the reference).  This translation unit
+// is compiled with -fmad=false so that no multiply-add is contracted; the reference (numpy) never fuses.
 //
 // Reference statements restated here (paths under PokerRL/):
 //   reach pass      game/_/tree/_/StrategyFiller.py:118-146, 148-169
@@ -14,238 +20,506 @@
 //   regrets         cfr/_CFRBase.py:146-185, cfr/CFRPlus.py:37-41, cfr/LinearCFR.py:27-31, cfr/VanillaCFR.py:26-30
 //   regret matching cfr/CFRPlus.py:43-63, cfr/LinearCFR.py:33-51, cfr/VanillaCFR.py:32-52
 //   averaging       cfr/CFRPlus.py:65-87, cfr/LinearCFR.py:53-76, cfr/VanillaCFR.py:54-77
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "pokerrl_b200.h"
 #include "prl_common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace {
+
+constexpr int kThreads = 128;
+constexpr int kChunk = 4;  // children whose rows are loaded together before use
+constexpr int kPThreads = 512;  // persistent kernels: ONE 512-thread block per SM keeps the grid barrier small
 
 struct Ctx {
     prl_tree_t T;
     prl_buffers_t B;
     int lo, hi;       // node range of this level
-    int mask;         // players to process
+    int mask;         // seats to process
     int mode[2];      // strategy source per seat
-    // CFR update parameters
-    int algo, upd_p, iter, delay, avg_f64;
+    int algo, upd_p, iter, delay, avg_f64;  // CFR update parameters
 };
+
+// ---- packed node record (see prl_pack_node_meta) ----------------------------------------------------------------
+struct Meta {
+    int first_child, first_slot;
+    float pot;
+    int kind, acted_last, board, n_children;
+};
+
+__device__ __forceinline__ Meta load_meta(const prl_tree_t& T, int n) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(T.meta) + n);
+    Meta m;
+    m.first_child = q.x;
+    m.first_slot = q.y;
+    m.pot = __int_as_float(q.z);
+    const unsigned w = (unsigned)q.w;
+    m.kind = w & 0xF;
+    m.acted_last = (int)((w >> 4) & 0x3) - 2;
+    m.board = (int)((w >> 8) & 0xFF) - 1;
+    m.n_children = (int)(w >> 16);
+    return m;
+}
+
+__global__ void pack_meta_kernel(prl_tree_t T, int4* out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= T.n_nodes) return;
+    const int fc = T.first_child[n];
+    const int k = T.kind[n];
+    int4 q;
+    q.x = fc;
+    q.y = (k <= PRL_KIND_P1 && fc >= 0) ? T.slot[fc] : -1;
+    q.z = __float_as_int(T.pot[n]);
+    const unsigned nc = (unsigned)T.n_children[n];
+    q.w = (int)((unsigned)k | ((unsigned)(T.acted_last[n] + 2) << 4) | ((unsigned)(T.board[n] + 1) << 8) | (nc << 16));
+    out[n] = q;
+}
+
+// ---- lane mapping -------------------------------------------------------------------------------------------------
+// One LANE per (node, hand): a warp holds NPW = 32 / R whole nodes (5 for Leduc's R = 6, lanes 30-31 idle; 1 for R = 24).
+// All per-lane state is scalar, the dependent chain of a lane is  work-list entry -> node record -> {children /
+// table elements, all issued together} -> stores, and the rows of a node are exchanged with group-masked shuffles.
+template <int R>
+struct LaneMap {
+    static constexpr int NPW = 32 / R;
+    int g, h, base;
+    unsigned gmask;
+    __device__ __forceinline__ LaneMap() {
+        const int lane = threadIdx.x & 31;
+        g = lane / R;
+        h = lane - g * R;
+        base = g * R;
+        gmask = ((R >= 32) ? 0xffffffffu : ((1u << R) - 1u)) << base;
+    }
+};
+
+__host__ __device__ __forceinline__ int groups_of(int nodes, int npw) { return (nodes + npw - 1) / npw; }
 
 __device__ __forceinline__ bool mode_is_f32(int m) { return m == PRL_STRAT_F32 || m == PRL_STRAT_AVG_F32; }
 
-// strategy probability of the child in table row `slot` (rows of the decision node start at first_slot, A rows)
-__device__ __forceinline__ float strat_f32(const Ctx& c, int m, int slot, int h) {
-    const float* tab = (m == PRL_STRAT_F32) ? c.B.strat : (const float*)c.B.avg;
-    return tab[(size_t)slot * c.T.ld + h];
-}
-
-__device__ __forceinline__ double strat_f64(const Ctx& c, int m, int slot, int first_slot, int A, int h) {
-    if (m == PRL_STRAT_UNIFORM64) return 1.0 / (double)A;
-    if (m == PRL_STRAT_AVG_F64) return ((const double*)c.B.avg)[(size_t)slot * c.T.ld + h];
-    // PRL_STRAT_AVG_SUM: float sums, float division, promoted to double (np.where with a float64 branch)
+// strategy probability of child k (row fs + k) for hand h in double, for the float64 sources
+__device__ __forceinline__ double strat_f64(const Ctx& c, int m, int fs, int k, int A, int h) {
+    const int ld = c.T.ld;
+    if (m == PRL_STRAT_UNIFORM64) return 1.0 / (double)A;  // StrategyFiller.py:61-62
+    if (m == PRL_STRAT_AVG_F64) return ((const double*)c.B.avg)[(size_t)(fs + k) * ld + h];
+    // PRL_STRAT_AVG_SUM: float sums / float division, promoted to double (LinearCFR.py:64-71)
     const float* tab = (const float*)c.B.avg;
-    float s = tab[(size_t)first_slot * c.T.ld + h];
-    for (int k = 1; k < A; ++k) s = s + tab[(size_t)(first_slot + k) * c.T.ld + h];
-    if (s == 0.0f) return 1.0 / (double)A;
-    return (double)(tab[(size_t)slot * c.T.ld + h] / s);
+    float tot = tab[(size_t)fs * ld + h];
+    for (int j = 1; j < A; ++j) tot = tot + tab[(size_t)(fs + j) * ld + h];
+    if (tot == 0.0f) return 1.0 / (double)A;
+    return (double)(tab[(size_t)(fs + k) * ld + h] / tot);
 }
 
-// one-card games: chance probability of dealing this node's board given hand h (StrategyFiller.py:159-166)
-__device__ __forceinline__ float chance_prob_1card(const Ctx& c, int n, int h) {
-    return (h == c.T.board[n]) ? 0.0f : (float)(1.0 / (double)(c.T.n_deck - 2));
-}
-
-__device__ __forceinline__ int leduc_rank(const Ctx& c, int h, int b) {
-    int r = h / c.T.n_suits;
-    return (b / c.T.n_suits == r) ? c.T.pair_bonus + r : r;
+// hand rank of card h on board card b (game_rules.py:68-75); NS = N_SUITS (compile time)
+template <int NS>
+__device__ __forceinline__ int card_rank(int h, int b, int pair_bonus) {
+    const int r = h / NS;
+    return (b / NS == r) ? pair_bonus + r : r;
 }
 
 // ------------------------------------------------------------------------------------------------ reach (top-down)
-template <bool UPDATE_AVG>
-__global__ void reach_level_kernel(Ctx c) {
-    const int R = c.T.n_range, ld = c.T.ld;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = c.lo + (int)(idx / R);
-    int h = (int)(idx % R);
-    if (n >= c.hi) return;
+// Lane = (parent node of level d, hand); writes element h of the reach rows of the children (level d+1).
+template <int R, bool UPDATE_AVG>
+__device__ __forceinline__ void reach_group(const Ctx& c, const int lo, const int hi, const int grp) {
+    const LaneMap<R> L;
+    const int t = lo + grp * LaneMap<R>::NPW + L.g;
+    if (L.g >= LaneMap<R>::NPW || t >= hi) return;
+    const int h = L.h;
+    const int n = __ldg(c.T.order + t);
+    const Meta m = load_meta(c.T, n);
     const size_t N = (size_t)c.T.n_nodes;
-    const int par = c.T.parent[n];
-#pragma unroll
+    const int ld = c.T.ld;
+    const int A = m.n_children, fc = m.first_child;
+#pragma unroll 1
     for (int q = 0; q < 2; ++q) {
         if (!(c.mask & (1 << q))) continue;
         float* reach_q = c.B.reach + (size_t)q * N * ld;
         float r;
-        if (par < 0) {
-            r = (float)(1.0 / (double)R);  // PublicTree.py:122-124
+        if (n == 0) {  // PublicTree.py:122-124
+            r = (float)(1.0 / (double)R);
+            reach_q[h] = r;
         } else {
-            const float rp = reach_q[(size_t)par * ld + h];
-            const int pk = c.T.kind[par];
-            if (pk == PRL_KIND_CHANCE) {
-                r = rp * chance_prob_1card(c, n, h);
-            } else if (pk == q) {
-                const int slot = c.T.slot[n];
-                const int m = c.mode[q];
-                if (mode_is_f32(m)) {
-                    const float s = strat_f32(c, m, slot, h);
-                    r = s * rp;
-                    if (UPDATE_AVG && q == c.upd_p) {
-                        if (c.algo == PRL_ALGO_CFR_PLUS) {
-                            if (c.iter >= c.delay) {
-                                // current_weight = sum(arange(delay+1, iter+1)); new_weight = iter - delay + 1
-                                const long long cw = ((long long)c.iter * (c.iter + 1) - (long long)c.delay * (c.delay + 1)) / 2;
-                                const long long nw = (long long)c.iter - c.delay + 1;
-                                double m_old = (double)cw / (double)(cw + nw);
-                                double m_new = (double)nw / (double)(cw + nw);
-                                if (c.iter == c.delay) { m_old = 0.0; m_new = 1.0; }
-                                if (c.avg_f64) {
-                                    double* a = (double*)c.B.avg + (size_t)slot * ld + h;
-                                    *a = m_old * (*a) + m_new * (double)s;
-                                } else {
-                                    float* a = (float*)c.B.avg + (size_t)slot * ld + h;
-                                    *a = (float)m_old * (*a) + (float)m_new * s;
-                                }
-                            }
-                        } else {
-                            float contrib = r;  // strategy * reach[p]
-                            if (c.algo == PRL_ALGO_LINEAR) contrib = contrib * (float)(c.iter + 1);
-                            float* a = (float*)c.B.avg + (size_t)slot * ld + h;
-                            *a = *a + contrib;
+            if (fc < 0) continue;
+            r = reach_q[(size_t)n * ld + h];
+        }
+        if (fc < 0) continue;
+        float* out = reach_q + (size_t)fc * ld + h;
+        if (m.kind == PRL_KIND_CHANCE) {  // StrategyFiller.py:137-140, 159-166 (child k deals card k)
+            const float cp = (float)(1.0 / (double)(c.T.n_deck - 2));
+            for (int k = 0; k < A; ++k) out[(size_t)k * ld] = r * ((h == k) ? 0.0f : cp);
+        } else if (m.kind == q) {  // StrategyFiller.py:129-134
+            const int md = c.mode[q];
+            const int fs = m.first_slot;
+            if (mode_is_f32(md)) {
+                const float* tab = ((md == PRL_STRAT_F32) ? c.B.strat : (const float*)c.B.avg) + (size_t)fs * ld + h;
+                const bool upd = UPDATE_AVG && q == c.upd_p;
+                double m_old = 0.0, m_new = 1.0;
+                if (upd && c.algo == PRL_ALGO_CFR_PLUS) {  // CFRPlus.py:68-73
+                    const long long cw = ((long long)c.iter * (c.iter + 1) - (long long)c.delay * (c.delay + 1)) / 2;
+                    const long long nw = (long long)c.iter - c.delay + 1;
+                    m_old = (double)cw / (double)(cw + nw);
+                    m_new = (double)nw / (double)(cw + nw);
+                }
+                const bool avg_f32 = upd && !(c.algo == PRL_ALGO_CFR_PLUS && (c.avg_f64 || c.iter < c.delay));
+                const bool avg_f64 = upd && c.algo == PRL_ALGO_CFR_PLUS && c.avg_f64 && c.iter >= c.delay;
+                float* avf = (float*)c.B.avg + (size_t)fs * ld + h;
+                double* avd = (double*)c.B.avg + (size_t)fs * ld + h;
+                const float w = (float)(c.iter + 1);
+                for (int k0 = 0; k0 < A; k0 += kChunk) {  // loads of a chunk first, then the stores
+                    float s[kChunk], av[kChunk];
+                    double ad[kChunk];
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) {
+                        if (k0 + j < A) {
+                            s[j] = tab[(size_t)(k0 + j) * ld];
+                            if (avg_f32) av[j] = avf[(size_t)(k0 + j) * ld];
+                            if (avg_f64) ad[j] = avd[(size_t)(k0 + j) * ld];
                         }
                     }
-                } else {
-                    const int fs = c.T.slot[c.T.first_child[par]];
-                    const double s = strat_f64(c, m, slot, fs, c.T.n_children[par], h);
-                    r = (float)(s * (double)rp);
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) {
+                        if (k0 + j < A) {
+                            const float x = s[j] * r;
+                            out[(size_t)(k0 + j) * ld] = x;
+                            if (avg_f64) {
+                                avd[(size_t)(k0 + j) * ld] = m_old * ad[j] + m_new * (double)s[j];
+                            } else if (avg_f32) {
+                                float a;
+                                if (c.algo == PRL_ALGO_CFR_PLUS) a = (float)m_old * av[j] + (float)m_new * s[j];
+                                else if (c.algo == PRL_ALGO_LINEAR) a = av[j] + x * w;  // LinearCFR.py:56-61
+                                else a = av[j] + x;                                      // VanillaCFR.py:57-62
+                                avf[(size_t)(k0 + j) * ld] = a;
+                            }
+                        }
+                    }
                 }
             } else {
-                r = rp;
+                for (int k = 0; k < A; ++k) out[(size_t)k * ld] = (float)(strat_f64(c, md, fs, k, A, h) * (double)r);
             }
+        } else {  // the other seat acts: reach of q is copied down
+            for (int k = 0; k < A; ++k) out[(size_t)k * ld] = r;
         }
-        reach_q[(size_t)n * ld + h] = r;
     }
 }
 
-// ------------------------------------------------------------------------------------------------ terminals (1 card)
-__device__ __forceinline__ float terminal_equity_1card(const Ctx& c, int n, int h, int p, int kind) {
-    const int R = c.T.n_range, ld = c.T.ld;
-    const float* ro = c.B.reach + ((size_t)(1 - p) * c.T.n_nodes + n) * ld;  // opponent reach row
-    const float K = (float)((double)c.T.n_deck / (double)(c.T.n_deck - 1));    // ValueFiller.py:19
-    const int b = c.T.board[n];
+// ------------------------------------------------------------------------------------------------ terminals
+// equity of hand h at a showdown on board card b against the opponent row ro[] (ValueFiller.py:140-155): sequential
+// float += / -= over opponent hands in ascending order
+template <int R, int NS>
+__device__ __forceinline__ float showdown_equity(const float (&ro)[R], int h, int b, int pair_bonus) {
+    const int rh = card_rank<NS>(h, b, pair_bonus);
+    float e = 0.0f;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int rj = card_rank<NS>(j, b, pair_bonus);
+        const bool live = (j != h) && (h != b) && (j != b);
+        if (live && rh > rj) e = e + ro[j];
+        else if (live && rh < rj) e = e - ro[j];
+    }
+    return e;
+}
+
+template <int R, int NS>
+__device__ __forceinline__ float terminal_value(const Ctx& c, const Meta& m, int n, int p, const LaneMap<R>& L) {
+    const int h = L.h;
+    const float mine = c.B.reach[((size_t)(1 - p) * c.T.n_nodes + n) * c.T.ld + h];  // opponent reach of MY hand index
+    float ro[R];  // the whole opponent row, gathered from the lanes of this node
+#pragma unroll
+    for (int j = 0; j < R; ++j) ro[j] = __shfl_sync(L.gmask, mine, L.base + j);
+    const float K = (float)((double)c.T.n_deck / (double)(c.T.n_deck - 1));  // ValueFiller.py:19
     float eq;
-    if (kind == PRL_KIND_FOLD) {  // ValueFiller.py:103-125
+    if (m.kind == PRL_KIND_FOLD) {  // ValueFiller.py:103-125
         float s = ro[0];
+#pragma unroll
         for (int j = 1; j < R; ++j) s = s + ro[j];
-        eq = s - ro[h];
-        if (c.T.acted_last[n] == p) eq = -eq;
+        eq = s - mine;
+        if (m.acted_last == p) eq = -eq;
         eq = eq * K;
-    } else if (kind == PRL_KIND_SHOWDOWN) {  // ValueFiller.py:127-158
-        eq = 0.0f;
-        if (h != b) {
-            const int rh = leduc_rank(c, h, b);
-            for (int j = 0; j < R; ++j) {
-                if (j == h || j == b) continue;
-                const int rj = leduc_rank(c, j, b);
-                if (rh > rj) eq = eq + ro[j];
-                else if (rh < rj) eq = eq - ro[j];
-            }
-        }
-        eq = eq * K;
+    } else if (m.kind == PRL_KIND_SHOWDOWN) {  // ValueFiller.py:127-158
+        eq = showdown_equity<R, NS>(ro, h, m.board, c.T.pair_bonus) * K;
     } else {  // all-in before the board card: ValueFiller.py:160-175
         eq = 0.0f;
-        for (int bb = 0; bb < c.T.n_deck; ++bb) {
-            float e = 0.0f;
-            if (h != bb) {
-                const int rh = leduc_rank(c, h, bb);
-                for (int j = 0; j < R; ++j) {
-                    if (j == h || j == bb) continue;
-                    const int rj = leduc_rank(c, j, bb);
-                    if (rh > rj) e = e + ro[j];
-                    else if (rh < rj) e = e - ro[j];
-                }
-            }
-            eq = eq + e * K;
-        }
+        for (int bb = 0; bb < c.T.n_deck; ++bb) eq = eq + showdown_equity<R, NS>(ro, h, bb, c.T.pair_bonus) * K;
         eq = eq / (float)(c.T.n_deck - 2);
     }
-    if (h == b) eq = 0.0f;  // ValueFiller.py:57-59
-    return eq;
+    if (h == m.board) eq = 0.0f;  // ValueFiller.py:57-59
+    return eq * m.pot / 2.0f;     // ValueFiller.py:61
+}
+
+// children elements combined in child order (sum, or max for the best response), loads issued chunk-wise up front
+template <bool MAX>
+__device__ __forceinline__ float fold_children(const float* __restrict__ col, int ld, int A) {
+    float v = 0.0f;
+    for (int k0 = 0; k0 < A; k0 += kChunk) {
+        float e[kChunk];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+            if (k0 + j < A) e[j] = col[(size_t)(k0 + j) * ld];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            if (k0 + j < A) {
+                if (k0 + j == 0) v = e[j];
+                else v = MAX ? fmaxf(v, e[j]) : v + e[j];
+            }
+        }
+    }
+    return v;
+}
+
+__device__ __forceinline__ float regret_step(int algo, float d, float old, float w) {
+    if (algo == PRL_ALGO_CFR_PLUS) return fmaxf(d + old, 0.0f);  // CFRPlus.py:37-41
+    if (algo == PRL_ALGO_LINEAR) return w * d + old;             // LinearCFR.py:27-31
+    return d + old;                                              // VanillaCFR.py:26-30
+}
+
+// Seat p acts at this node and is being updated, A children (compile time): node value with the current strategy,
+// regret update (_CFRBase.py:146-185) and regret matching (CFRPlus.py:43-63 and siblings).  Everything the lane needs
+// is requested before the first use; returns the node value.
+template <int A>
+__device__ __forceinline__ float update_own(const Ctx& c, int md, const float* __restrict__ ecol, int fs, int h) {
+    const int ld = c.T.ld;
+    float* rcol = c.B.regret + (size_t)fs * ld + h;
+    float* scol = c.B.strat + (size_t)fs * ld + h;
+    const bool f32 = mode_is_f32(md);
+    const float* tab = ((md == PRL_STRAT_AVG_F32) ? (const float*)c.B.avg : c.B.strat) + (size_t)fs * ld + h;
+    float e[A], rg[A], sg[A];
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        e[k] = ecol[k * ld];
+        rg[k] = rcol[k * ld];
+        sg[k] = f32 ? tab[k * ld] : 0.0f;
+    }
+    float v;
+    if (f32) {
+        v = sg[0] * e[0];
+#pragma unroll
+        for (int k = 1; k < A; ++k) v = v + sg[k] * e[k];
+    } else {
+        double acc = strat_f64(c, md, fs, 0, A, h) * (double)e[0];
+#pragma unroll
+        for (int k = 1; k < A; ++k) acc = acc + strat_f64(c, md, fs, k, A, h) * (double)e[k];
+        v = (float)acc;
+    }
+    const float w = (float)(c.iter + 1);
+    float ssum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        rg[k] = regret_step(c.algo, e[k] - v, rg[k], w);
+        const float rp = fmaxf(rg[k], 0.0f);
+        ssum = (k == 0) ? rp : ssum + rp;
+    }
+    const float uni = (float)(1.0 / (double)A);
+    const float den = (ssum > 0.0f) ? ssum : 1.0f;  // keeps div.rn off its slow path when the positive mass is 0
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        rcol[k * ld] = rg[k];
+        const float q = fmaxf(rg[k], 0.0f) / den;
+        scol[k * ld] = (ssum > 0.0f) ? q : uni;
+    }
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------ value (bottom-up)
-template <bool WITH_BR, bool UPDATE>
-__global__ void value_level_kernel(Ctx c) {
-    const int R = c.T.n_range, ld = c.T.ld;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = c.lo + (int)(idx / R);
-    int h = (int)(idx % R);
-    if (n >= c.hi) return;
+// Lane = (node of level d, hand); reads element h of its children's rows (level d+1).
+template <int R, int NS, bool WITH_BR, bool UPDATE>
+__device__ __forceinline__ void value_group(const Ctx& c, const int lo, const int hi, const int grp) {
+    constexpr int kRegA = 8;  // children of an updated node kept in registers (wider nodes stream)
+    const LaneMap<R> L;
+    const int t = lo + grp * LaneMap<R>::NPW + L.g;
+    if (L.g >= LaneMap<R>::NPW || t >= hi) return;
+    const int h = L.h;
+    const int n = __ldg(c.T.order + t);
+    const Meta m = load_meta(c.T, n);
     const size_t N = (size_t)c.T.n_nodes;
-    const int kind = c.T.kind[n];
-    const int fc = c.T.first_child[n];
-    const int A = c.T.n_children[n];
-#pragma unroll
+    const int ld = c.T.ld;
+    const int A = m.n_children, fc = m.first_child;
+#pragma unroll 1
     for (int p = 0; p < 2; ++p) {
         if (!(c.mask & (1 << p))) continue;
         float* ev_p = c.B.ev + (size_t)p * N * ld;
         float* evbr_p = WITH_BR ? c.B.ev_br + (size_t)p * N * ld : nullptr;
         float v, vbr = 0.0f;
-        if (kind >= PRL_KIND_FOLD) {
-            const float eq = terminal_equity_1card(c, n, h, p, kind);
-            v = eq * c.T.pot[n] / 2.0f;  // ValueFiller.py:61
+        if (m.kind >= PRL_KIND_FOLD) {
+            v = terminal_value<R, NS>(c, m, n, p, L);
             vbr = v;
-        } else if (kind == PRL_KIND_CHANCE || kind != p) {
-            // chance node, or the opponent acts: plain sum over children (ValueFiller.py:76-78, 88-90)
-            v = ev_p[(size_t)fc * ld + h];
-            for (int k = 1; k < A; ++k) v = v + ev_p[(size_t)(fc + k) * ld + h];
-            if (WITH_BR) {
-                vbr = evbr_p[(size_t)fc * ld + h];
-                for (int k = 1; k < A; ++k) vbr = vbr + evbr_p[(size_t)(fc + k) * ld + h];
-            }
+        } else if (m.kind == PRL_KIND_CHANCE || m.kind != p) {
+            // chance node, or the other seat acts: plain sums over children (ValueFiller.py:76-78, 88-90)
+            v = fold_children<false>(ev_p + (size_t)fc * ld + h, ld, A);
+            if (WITH_BR) vbr = fold_children<false>(evbr_p + (size_t)fc * ld + h, ld, A);
         } else {
-            // p acts here (ValueFiller.py:87, 91)
-            const int fs = c.T.slot[fc];
-            const int m = c.mode[p];
-            if (mode_is_f32(m)) {
-                v = strat_f32(c, m, fs, h) * ev_p[(size_t)fc * ld + h];
-                for (int k = 1; k < A; ++k) v = v + strat_f32(c, m, fs + k, h) * ev_p[(size_t)(fc + k) * ld + h];
-            } else {
-                double acc = strat_f64(c, m, fs, fs, A, h) * (double)ev_p[(size_t)fc * ld + h];
-                for (int k = 1; k < A; ++k)
-                    acc = acc + strat_f64(c, m, fs + k, fs, A, h) * (double)ev_p[(size_t)(fc + k) * ld + h];
-                v = (float)acc;
-            }
-            if (WITH_BR) {
-                vbr = evbr_p[(size_t)fc * ld + h];
-                for (int k = 1; k < A; ++k) vbr = fmaxf(vbr, evbr_p[(size_t)(fc + k) * ld + h]);
-            }
-            if (UPDATE && p == c.upd_p) {
-                // regret update (_CFRBase.py:146-185) then regret matching into the strategy table
-                float* reg = c.B.regret;
-                float* st = c.B.strat;
-                const float w = (float)(c.iter + 1);
-                float s = 0.0f;
-                for (int k = 0; k < A; ++k) {
-                    const size_t off = (size_t)(fs + k) * ld + h;
-                    const float d = ev_p[(size_t)(fc + k) * ld + h] - v;
-                    float r;
-                    if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + reg[off], 0.0f);
-                    else if (c.algo == PRL_ALGO_LINEAR) r = w * d + reg[off];
-                    else r = d + reg[off];
-                    reg[off] = r;
-                    const float rp = fmaxf(r, 0.0f);
-                    s = (k == 0) ? rp : s + rp;
+            // seat p acts here (ValueFiller.py:87, 91)
+            const int fs = m.first_slot;
+            const int md = c.mode[p];
+            const float* ecol = ev_p + (size_t)fc * ld + h;
+            if (WITH_BR) vbr = fold_children<true>(evbr_p + (size_t)fc * ld + h, ld, A);
+            const bool upd = UPDATE && p == c.upd_p;
+            if (upd && A <= kRegA) {
+                // warps are uniform in A (work list sorted by kind, n_children): jump to the exactly-unrolled variant
+                switch (A) {
+                    case 1: v = update_own<1>(c, md, ecol, fs, h); break;
+                    case 2: v = update_own<2>(c, md, ecol, fs, h); break;
+                    case 3: v = update_own<3>(c, md, ecol, fs, h); break;
+                    case 4: v = update_own<4>(c, md, ecol, fs, h); break;
+                    case 5: v = update_own<5>(c, md, ecol, fs, h); break;
+                    case 6: v = update_own<6>(c, md, ecol, fs, h); break;
+                    case 7: v = update_own<7>(c, md, ecol, fs, h); break;
+                    default: v = update_own<8>(c, md, ecol, fs, h); break;
                 }
-                const float uni = (float)(1.0 / (double)A);
-                for (int k = 0; k < A; ++k) {
-                    const size_t off = (size_t)(fs + k) * ld + h;
-                    st[off] = (s > 0.0f) ? fmaxf(reg[off], 0.0f) / s : uni;
+            } else {
+                if (mode_is_f32(md)) {
+                    const float* tab = ((md == PRL_STRAT_F32) ? c.B.strat : (const float*)c.B.avg) + (size_t)fs * ld + h;
+                    v = 0.0f;
+                    for (int k0 = 0; k0 < A; k0 += kChunk) {
+                        float s[kChunk], e[kChunk];
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j) {
+                            if (k0 + j < A) {
+                                s[j] = tab[(size_t)(k0 + j) * ld];
+                                e[j] = ecol[(size_t)(k0 + j) * ld];
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j)
+                            if (k0 + j < A) v = (k0 + j == 0) ? s[j] * e[j] : v + s[j] * e[j];
+                    }
+                } else {
+                    double acc = 0.0;
+                    for (int k = 0; k < A; ++k) {
+                        const double sk = strat_f64(c, md, fs, k, A, h);
+                        acc = (k == 0) ? sk * (double)ecol[(size_t)k * ld] : acc + sk * (double)ecol[(size_t)k * ld];
+                    }
+                    v = (float)acc;
+                }
+                if (upd) {  // wide node: stream (regrets are recomputed in the second loop instead of re-read)
+                    float* rcol = c.B.regret + (size_t)fs * ld + h;
+                    float* scol = c.B.strat + (size_t)fs * ld + h;
+                    const float w = (float)(c.iter + 1);
+                    float ssum = 0.0f;
+                    for (int k = 0; k < A; ++k) {
+                        const float rp = fmaxf(regret_step(c.algo, ecol[(size_t)k * ld] - v, rcol[(size_t)k * ld], w), 0.0f);
+                        ssum = (k == 0) ? rp : ssum + rp;
+                    }
+                    const float uni = (float)(1.0 / (double)A);
+                    const float den = (ssum > 0.0f) ? ssum : 1.0f;
+                    for (int k = 0; k < A; ++k) {
+                        const float r = regret_step(c.algo, ecol[(size_t)k * ld] - v, rcol[(size_t)k * ld], w);
+                        rcol[(size_t)k * ld] = r;
+                        const float q = fmaxf(r, 0.0f) / den;
+                        scol[(size_t)k * ld] = (ssum > 0.0f) ? q : uni;
+                    }
                 }
             }
         }
         ev_p[(size_t)n * ld + h] = v;
         if (WITH_BR) evbr_p[(size_t)n * ld + h] = vbr;
     }
+}
+
+// ---- one launch per level (any tree size): one warp per group of NPW nodes --------------------------------------------
+template <int R, bool UPDATE_AVG>
+__global__ void __launch_bounds__(kThreads) reach_level_kernel(const Ctx c) {
+    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (grp < groups_of(c.hi - c.lo, LaneMap<R>::NPW)) reach_group<R, UPDATE_AVG>(c, c.lo, c.hi, grp);
+}
+
+template <int R, int NS, bool WITH_BR, bool UPDATE>
+__global__ void __launch_bounds__(kThreads) value_level_kernel(const Ctx c) {
+    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (grp < groups_of(c.hi - c.lo, LaneMap<R>::NPW)) value_group<R, NS, WITH_BR, UPDATE>(c, c.lo, c.hi, grp);
+}
+
+// ---- persistent cooperative kernels: whole sweeps / iterations in ONE launch, grid barrier between levels ------------
+// (one launch instead of 4 x n_levels per iteration: no launch gaps, instruction cache stays warm, L1 is invalidated by
+// the gpu-scope fence inside grid.sync())
+constexpr int kMaxLevels = 40;
+struct Levels {
+    int n_levels;
+    int start[kMaxLevels + 1];
+    int nonterm[kMaxLevels];
+    unsigned long long* timeline;  // optional (prl_debug_set_timeline): %globaltimer after every grid barrier
+};
+
+__device__ __forceinline__ void stamp(const Levels& lv, int& slot) {
+    if (lv.timeline && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        lv.timeline[slot] = t;
+    }
+    ++slot;
+}
+
+__device__ __forceinline__ void root_exploitability(const prl_tree_t& T, const prl_buffers_t& B, int p, float* out) {
+    const size_t N = (size_t)T.n_nodes;
+    const float* ev = B.ev + (size_t)p * N * T.ld;
+    const float* evbr = B.ev_br + (size_t)p * N * T.ld;
+    const float* reach = B.reach + (size_t)p * N * T.ld;
+    float s = 0.0f;
+    for (int h = 0; h < T.n_range; ++h) {
+        const float e = evbr[h] * reach[h] - ev[h] * reach[h];
+        s = (h == 0) ? e : s + e;
+    }
+    out[p] = s;
+}
+
+template <int R, int NS>
+__global__ void __launch_bounds__(kPThreads, 1) cfr_iterations_kernel(Ctx c, const Levels lv, const int n_iters) {
+    cg::grid_group grid = cg::this_grid();
+    // warp w of block b takes 32-entry chunk (w * gridDim + b) of the kind-sorted work list: consecutive chunks go to
+    // different SMs, so every SM sees the same mix of node kinds (no per-kind load imbalance at the grid barrier)
+    const int gwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    constexpr int NPW = LaneMap<R>::NPW;
+    const int last = lv.n_levels > 1 ? lv.n_levels - 1 : 1;
+    int ts = 0;
+    stamp(lv, ts);
+    for (int it = 0; it < n_iters; ++it) {
+        for (int p = 0; p < 2; ++p) {  // _CFRBase.py:123-128
+            c.mask = 1 << p;
+            c.upd_p = p;
+            for (int d = lv.n_levels - 1; d >= 0; --d) {
+                const int lo = lv.start[d], hi = lv.start[d + 1], ng = groups_of(hi - lo, NPW);
+                for (int grp = gwarp; grp < ng; grp += nwarps) value_group<R, NS, false, true>(c, lo, hi, grp);
+                grid.sync();
+                stamp(lv, ts);
+            }
+            c.mode[p] = PRL_STRAT_F32;
+            for (int d = 0; d < last; ++d) {
+                const int lo = lv.start[d], hi = lo + lv.nonterm[d], ng = groups_of(hi - lo, NPW);
+                for (int grp = gwarp; grp < ng; grp += nwarps) reach_group<R, true>(c, lo, hi, grp);
+                grid.sync();
+                stamp(lv, ts);
+            }
+        }
+        c.iter += 1;
+    }
+}
+
+template <int R, int NS>
+__global__ void __launch_bounds__(kPThreads, 1) evaluate_kernel(Ctx c, const Levels lv, const int do_reach, float* out) {
+    cg::grid_group grid = cg::this_grid();
+    const int gwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    constexpr int NPW = LaneMap<R>::NPW;
+    const int last = lv.n_levels > 1 ? lv.n_levels - 1 : 1;
+    c.mask = 3;
+    c.upd_p = -1;
+    if (do_reach) {
+        for (int d = 0; d < last; ++d) {
+            const int lo = lv.start[d], hi = lo + lv.nonterm[d], ng = groups_of(hi - lo, NPW);
+            for (int grp = gwarp; grp < ng; grp += nwarps) reach_group<R, false>(c, lo, hi, grp);
+            grid.sync();
+        }
+    }
+    for (int d = lv.n_levels - 1; d >= 0; --d) {
+        const int lo = lv.start[d], hi = lv.start[d + 1], ng = groups_of(hi - lo, NPW);
+        for (int grp = gwarp; grp < ng; grp += nwarps) value_group<R, NS, true, false>(c, lo, hi, grp);
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 2) root_exploitability(c.T, c.B, threadIdx.x, out);
 }
 
 // root exploitability (ValueFiller.py:95-101): sequential float sums like numpy's short contiguous reduction
@@ -264,31 +538,79 @@ __global__ void root_exploitability_kernel(prl_tree_t T, prl_buffers_t B, float*
     out[p] = s;
 }
 
-constexpr int kThreads = 256;
+// one warp per group of `npw` nodes
+inline unsigned grid_for(int n_nodes, int npw) {
+    const long long threads = 32LL * groups_of(n_nodes, npw);
+    return (unsigned)((threads + kThreads - 1) / kThreads);
+}
 
-#define PRL_LAUNCH(kernel, grid, stream, ...) do { kernel<<<(grid), kThreads, 0, (stream)>>>(__VA_ARGS__); prl::count_launch(); } while (0)
-
-inline unsigned grid_for(long long n_threads) { return (unsigned)((n_threads + kThreads - 1) / kThreads); }
+#define PRL_LAUNCH(kernel, nodes, npw, stream, ...)                              \
+    do {                                                                         \
+        kernel<<<grid_for(nodes, npw), kThreads, 0, (stream)>>>(__VA_ARGS__);    \
+        prl::count_launch();                                                     \
+    } while (0)
 
 int check_tree(const prl_tree_t* t) {
-    if (!t || !t->level_start || t->n_hole != 1) return prl::fail("prl: level sweeps support one-hole-card games (n_hole == 1)");
+    if (!t || !t->level_start) return prl::fail("prl: null tree / level_start");
+    if (t->n_hole != 1) return prl::fail("prl: these sweeps serve one-hole-card games (n_hole == 1)");
+    if (!t->meta) return prl::fail("prl: tree.meta is NULL (call prl_pack_node_meta once after uploading the tree)");
+    if (!t->order || !t->level_nonterm) return prl::fail("prl: tree.order / level_nonterm missing");
+    if (t->n_suits != 2 || (t->n_range != 6 && t->n_range != 24) || t->n_deck != t->n_range)
+        return prl::fail("prl: one-card kernels are instantiated for Leduc (R=6) and BigLeduc (R=24), 2 suits");
     return 0;
 }
 
+template <int R>
+void launch_reach(const Ctx& c, int nodes, bool update_avg, cudaStream_t s) {
+    if (update_avg) PRL_LAUNCH((reach_level_kernel<R, true>), nodes, LaneMap<R>::NPW, s, c);
+    else PRL_LAUNCH((reach_level_kernel<R, false>), nodes, LaneMap<R>::NPW, s, c);
+}
+
+template <int R>
+void launch_value(const Ctx& c, int nodes, bool with_br, bool update, cudaStream_t s) {
+    if (update) PRL_LAUNCH((value_level_kernel<R, 2, false, true>), nodes, LaneMap<R>::NPW, s, c);
+    else if (with_br) PRL_LAUNCH((value_level_kernel<R, 2, true, false>), nodes, LaneMap<R>::NPW, s, c);
+    else PRL_LAUNCH((value_level_kernel<R, 2, false, false>), nodes, LaneMap<R>::NPW, s, c);
+}
+
+void reach_sweep(Ctx c, bool update_avg, cudaStream_t s) {
+    const prl_tree_t& T = c.T;
+    const int last = T.n_levels > 1 ? T.n_levels - 1 : 1;  // parents of level d write level d+1; leaves write nothing
+    for (int d = 0; d < last; ++d) {
+        c.lo = (int)T.level_start[d];
+        c.hi = c.lo + (int)T.level_nonterm[d];  // the work list puts terminals last: they have nothing to push down
+        if (c.hi == c.lo) continue;
+        if (T.n_range == 6) launch_reach<6>(c, c.hi - c.lo, update_avg, s);
+        else launch_reach<24>(c, c.hi - c.lo, update_avg, s);
+    }
+}
+
+void value_sweep(Ctx c, bool with_br, bool update, cudaStream_t s) {
+    const prl_tree_t& T = c.T;
+    for (int d = T.n_levels - 1; d >= 0; --d) {
+        c.lo = (int)T.level_start[d];
+        c.hi = (int)T.level_start[d + 1];
+        if (c.hi == c.lo) continue;
+        if (T.n_range == 6) launch_value<6>(c, c.hi - c.lo, with_br, update, s);
+        else launch_value<24>(c, c.hi - c.lo, with_br, update, s);
+    }
+}
+
 }  // namespace
+
+extern "C" int prl_pack_node_meta(const prl_tree_t* tree, void* out_meta, prl_stream_t stream) {
+    if (!tree || !out_meta) return prl::fail("prl_pack_node_meta: null argument");
+    if (tree->n_hole == 1 && tree->n_deck > 254) return prl::fail("prl_pack_node_meta: deck too large");
+    pack_meta_kernel<<<(tree->n_nodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*tree, (int4*)out_meta);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_pack_node_meta");
+}
 
 extern "C" int prl_reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, const int* strat_mode,
                               prl_stream_t stream) {
     if (int e = check_tree(tree)) return e;
     Ctx c{*tree, *buf, 0, 0, player_mask, {strat_mode[0], strat_mode[1]}, 0, -1, 0, 0, 0};
-    cudaStream_t s = (cudaStream_t)stream;
-    for (int d = 0; d < tree->n_levels; ++d) {
-        c.lo = (int)tree->level_start[d];
-        c.hi = (int)tree->level_start[d + 1];
-        long long nt = (long long)(c.hi - c.lo) * tree->n_range;
-        if (nt == 0) continue;
-        PRL_LAUNCH(reach_level_kernel<false>, grid_for(nt), s, c);
-    }
+    reach_sweep(c, false, (cudaStream_t)stream);
     return prl::check(cudaGetLastError(), "prl_reach_pass");
 }
 
@@ -297,15 +619,7 @@ extern "C" int prl_value_pass(const prl_tree_t* tree, const prl_buffers_t* buf, 
     if (int e = check_tree(tree)) return e;
     if (with_br && !buf->ev_br) return prl::fail("prl_value_pass: with_br needs ev_br");
     Ctx c{*tree, *buf, 0, 0, player_mask, {strat_mode[0], strat_mode[1]}, 0, -1, 0, 0, 0};
-    cudaStream_t s = (cudaStream_t)stream;
-    for (int d = tree->n_levels - 1; d >= 0; --d) {
-        c.lo = (int)tree->level_start[d];
-        c.hi = (int)tree->level_start[d + 1];
-        long long nt = (long long)(c.hi - c.lo) * tree->n_range;
-        if (nt == 0) continue;
-        if (with_br) PRL_LAUNCH((value_level_kernel<true, false>), grid_for(nt), s, c);
-        else PRL_LAUNCH((value_level_kernel<false, false>), grid_for(nt), s, c);
-    }
+    value_sweep(c, with_br != 0, false, (cudaStream_t)stream);
     return prl::check(cudaGetLastError(), "prl_value_pass");
 }
 
@@ -323,27 +637,90 @@ extern "C" int prl_cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, i
     if (p < 0 || p > 1 || algo < 0 || algo > 2) return prl::fail("prl_cfr_sweep: bad p / algo");
     if (algo != PRL_ALGO_CFR_PLUS && avg_f64) return prl::fail("avg_f64 only applies to CFR+");
     Ctx c{*tree, *buf, 0, 0, 1 << p, {strat_mode[0], strat_mode[1]}, algo, p, iter, delay, avg_f64};
-    cudaStream_t s = (cudaStream_t)stream;
-    if (which & 1) {
-        for (int d = tree->n_levels - 1; d >= 0; --d) {
-            c.lo = (int)tree->level_start[d];
-            c.hi = (int)tree->level_start[d + 1];
-            long long nt = (long long)(c.hi - c.lo) * tree->n_range;
-            if (nt == 0) continue;
-            PRL_LAUNCH((value_level_kernel<false, true>), grid_for(nt), s, c);
-        }
-    }
+    if (which & 1) value_sweep(c, false, true, (cudaStream_t)stream);
     if (which & 2) {
         c.mode[p] = PRL_STRAT_F32;  // p's strategy now lives in the float table
-        for (int d = 0; d < tree->n_levels; ++d) {
-            c.lo = (int)tree->level_start[d];
-            c.hi = (int)tree->level_start[d + 1];
-            long long nt = (long long)(c.hi - c.lo) * tree->n_range;
-            if (nt == 0) continue;
-            PRL_LAUNCH(reach_level_kernel<true>, grid_for(nt), s, c);
-        }
+        reach_sweep(c, true, (cudaStream_t)stream);
     }
     return prl::check(cudaGetLastError(), "prl_cfr_sweep");
+}
+
+namespace {
+
+unsigned long long* g_timeline = nullptr;
+
+int make_levels(const prl_tree_t* T, Levels* lv) {
+    lv->timeline = g_timeline;
+    if (T->n_levels > kMaxLevels) return prl::fail("prl: tree deeper than the persistent kernels support");
+    lv->n_levels = T->n_levels;
+    for (int d = 0; d <= T->n_levels; ++d) lv->start[d] = (int)T->level_start[d];
+    for (int d = 0; d < T->n_levels; ++d) lv->nonterm[d] = (int)T->level_nonterm[d];
+    return 0;
+}
+
+// co-resident grid for a cooperative launch of `kernel` (cached per kernel and device)
+template <typename K>
+int coop_grid(K kernel, int* grid) {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && cached[dev]) { *grid = cached[dev]; return 0; }
+    int per_sm = 0, sms = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPThreads, 0);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return prl::check(e, "cooperative occupancy query");
+    if (per_sm < 1) return prl::fail("prl: persistent kernel does not fit on an SM");
+    *grid = sms;  // one block per SM
+    if (dev < 64) cached[dev] = *grid;
+    return 0;
+}
+
+template <int R>
+int launch_iterations(Ctx& c, Levels& lv, int n_iters, cudaStream_t s) {
+    int grid = 0;
+    if (int e = coop_grid(cfr_iterations_kernel<R, 2>, &grid)) return e;
+    void* args[] = {&c, &lv, &n_iters};
+    prl::count_launch();
+    return prl::check(cudaLaunchCooperativeKernel((void*)cfr_iterations_kernel<R, 2>, dim3(grid), dim3(kPThreads), args, 0, s),
+                      "prl_cfr_iterations");
+}
+
+template <int R>
+int launch_evaluate(Ctx& c, Levels& lv, int do_reach, float* out, cudaStream_t s) {
+    int grid = 0;
+    if (int e = coop_grid(evaluate_kernel<R, 2>, &grid)) return e;
+    void* args[] = {&c, &lv, &do_reach, &out};
+    prl::count_launch();
+    return prl::check(cudaLaunchCooperativeKernel((void*)evaluate_kernel<R, 2>, dim3(grid), dim3(kPThreads), args, 0, s),
+                      "prl_evaluate");
+}
+
+}  // namespace
+
+extern "C" void prl_debug_set_timeline(void* device_u64_buffer) { g_timeline = (unsigned long long*)device_u64_buffer; }
+
+extern "C" int prl_cfr_iterations(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int iter0, int n_iters,
+                                  int delay, int avg_f64, const int* strat_mode, prl_stream_t stream) {
+    if (int e = check_tree(tree)) return e;
+    if (algo < 0 || algo > 2 || n_iters < 0) return prl::fail("prl_cfr_iterations: bad algo / n_iters");
+    if (algo != PRL_ALGO_CFR_PLUS && avg_f64) return prl::fail("avg_f64 only applies to CFR+");
+    if (n_iters == 0) return 0;
+    Ctx c{*tree, *buf, 0, 0, 0, {strat_mode[0], strat_mode[1]}, algo, 0, iter0, delay, avg_f64};
+    Levels lv;
+    if (int e = make_levels(tree, &lv)) return e;
+    return tree->n_range == 6 ? launch_iterations<6>(c, lv, n_iters, (cudaStream_t)stream)
+                              : launch_iterations<24>(c, lv, n_iters, (cudaStream_t)stream);
+}
+
+extern "C" int prl_evaluate(const prl_tree_t* tree, const prl_buffers_t* buf, const int* strat_mode, int do_reach,
+                            float* out_expl, prl_stream_t stream) {
+    if (int e = check_tree(tree)) return e;
+    if (!buf->ev_br || !out_expl) return prl::fail("prl_evaluate needs ev_br and out_expl");
+    Ctx c{*tree, *buf, 0, 0, 3, {strat_mode[0], strat_mode[1]}, 0, -1, 0, 0, 0};
+    Levels lv;
+    if (int e = make_levels(tree, &lv)) return e;
+    return tree->n_range == 6 ? launch_evaluate<6>(c, lv, do_reach, out_expl, (cudaStream_t)stream)
+                              : launch_evaluate<24>(c, lv, do_reach, out_expl, (cudaStream_t)stream);
 }
 
 extern "C" int prl_cfr_half_iteration(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter,

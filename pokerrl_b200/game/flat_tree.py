@@ -291,6 +291,18 @@ class FlatTree:
         out[m] = bc[self.board[m]]
         return out
 
+    def work_order(self):
+        """(order, level_nonterm): per level the node ids sorted by (kind, n_children), non-terminals first, so that
+        a warp of the GPU sweeps holds nodes of one kind; level_nonterm[d] = number of non-terminals of level d."""
+        order = np.empty(self.n_nodes, np.int32)
+        level_nonterm = np.zeros(self.n_levels, np.int64)
+        key = self.kind.astype(np.int64) * 4096 + self.n_children.astype(np.int64)
+        for d in range(self.n_levels):
+            lo, hi = int(self.level_start[d]), int(self.level_start[d + 1])
+            order[lo:hi] = lo + np.argsort(key[lo:hi], kind="stable")
+            level_nonterm[d] = int((self.kind[lo:hi] <= KIND_CHANCE).sum())
+        return order, level_nonterm
+
     def dfs_permutation(self):
         """perm such that array_in_dfs_order = array_in_flat_order[perm]"""
         perm = np.empty(self.n_nodes, np.int64)

@@ -5,6 +5,7 @@ This is the engine behind the reference-shaped façades in `pokerrl_b200.cfr` / 
 iteration schedule of `PokerRL/cfr/_CFRBase.py:110-134`.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -32,6 +33,7 @@ class DeviceTree:
         self.device = _require_cuda(device)
         rules = ft.rules
         self.R = ft.R
+        # row stride = R (measured on B200: padding Leduc rows 6 -> 8 floats to whole 32-byte sectors was 8 % slower)
         self.ld = ft.R
         dev = self.device
 
@@ -63,7 +65,22 @@ class DeviceTree:
         d.n_children, d.slot = self.t_n_children.data_ptr(), self.t_slot.data_ptr()
         d.kind, d.acted_last = self.t_kind.data_ptr(), self.t_acted_last.data_ptr()
         d.pot, d.board = self.t_pot.data_ptr(), self.t_board.data_ptr()
+        order, level_nonterm = ft.work_order()
+        self.t_order = up(order, np.int32)
+        self._level_nonterm = np.ascontiguousarray(level_nonterm, dtype=np.int64)
+        d.order, d.level_nonterm = self.t_order.data_ptr(), self._level_nonterm.ctypes.data
+        d.meta = None
         self.desc = d
+        if rules.N_HOLE_CARDS == 1:
+            # the one-card kernels assume chance child k deals card k (boards ascending, PublicTree.py:193-203)
+            ch = np.nonzero(ft.kind == nat.KIND_CHANCE)[0]
+            assert np.all(ft.n_children[ch] == rules.N_CARDS_IN_DECK)
+            fc0 = ft.first_child[ch[0]] if ch.size else 0
+            assert ch.size == 0 or np.array_equal(board[fc0:fc0 + rules.N_CARDS_IN_DECK],
+                                                  np.arange(rules.N_CARDS_IN_DECK))
+        self.t_meta = torch.zeros(ft.n_nodes, 4, dtype=torch.int32, device=dev)
+        nat.call("prl_pack_node_meta", C.byref(d), C.c_void_p(self.t_meta.data_ptr()), _stream())
+        d.meta = self.t_meta.data_ptr()
 
     @property
     def n_nodes(self):
@@ -112,6 +129,12 @@ class TreeOps:
         nat.call("prl_value_pass", C.byref(self.dtree.desc), C.byref(self.bufs.desc), player_mask, int(with_br),
                  nat.modes(*modes), _stream())
 
+    def evaluate(self, modes, do_reach):
+        """One persistent launch: [reach pass,] value pass with BR, root exploitability -> float32[2] chips."""
+        nat.call("prl_evaluate", C.byref(self.dtree.desc), C.byref(self.bufs.desc), nat.modes(*modes), int(do_reach),
+                 C.c_void_p(self._expl.data_ptr()), _stream())
+        return self._expl.cpu().numpy()
+
     def root_exploitability(self):
         """float32[2] chips (device->host read)."""
         nat.call("prl_root_exploitability", C.byref(self.dtree.desc), C.byref(self.bufs.desc),
@@ -127,7 +150,8 @@ class CFRSolver:
     strategy is a separate, optional evaluation (the reference does both every iteration).
     """
 
-    def __init__(self, ft, algo="CFRPlus", delay=0, device=None, avg_f64=False):
+    def __init__(self, ft, algo="CFRPlus", delay=0, device=None, avg_f64=False, persistent=True):
+        self.persistent = bool(persistent)  # one cooperative launch per call instead of one launch per tree level
         self.algo_name = algo
         self.algo = ALGOS[algo]
         self.delay = int(delay) if algo == "CFRPlus" else 0
@@ -148,6 +172,12 @@ class CFRSolver:
 
     def iteration(self, n=1):
         tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
+        if self.persistent and n > 0:
+            nat.call("prl_cfr_iterations", tree, buf, self.algo, self.iter_counter, n, self.delay,
+                     int(self.avg_f64), nat.modes(*self.modes), _stream())
+            self.modes = [nat.STRAT_F32, nat.STRAT_F32]
+            self.iter_counter += n
+            return
         for _ in range(n):
             for p in (0, 1):
                 nat.call("prl_cfr_half_iteration", tree, buf, self.algo, p, self.iter_counter, self.delay,
@@ -161,6 +191,8 @@ class CFRSolver:
         return sum(e) / 2
 
     def exploitability_current(self):
+        if self.persistent:
+            return self._metric(self.ops.evaluate(self.modes, do_reach=False))
         self.ops.value_pass(self.modes, 3, True)
         return self._metric(self.ops.root_exploitability())
 
@@ -179,6 +211,8 @@ class CFRSolver:
             self._eval_bufs = TreeBuffers(self.dtree, share=self.bufs)
             self._eval_ops = TreeOps(self.dtree, self._eval_bufs)
         m = self.average_modes()
+        if self.persistent:
+            return self._metric(self._eval_ops.evaluate(m, do_reach=True))
         self._eval_ops.reach_pass(m)
         self._eval_ops.value_pass(m, 3, True)
         return self._metric(self._eval_ops.root_exploitability())

@@ -68,11 +68,12 @@ def test_b3_uniform_root():
     ("LinearCFR", "NLLeduc_POT"), ("LinearCFR", "StandardLeduc"),
     ("VanillaCFR", "NLLeduc_POT"), ("VanillaCFR", "StandardLeduc"),
 ])
-def test_cfr_trajectory_bit_exact(algo, name):
+@pytest.mark.parametrize("persistent", [True, False])
+def test_cfr_trajectory_bit_exact(algo, name, persistent):
     from pokerrl_b200.solver import CFRSolver
     ft = make_flat_tree(name)
     g = golden("cfr_%s_%s.npz" % (algo, name))
-    s = CFRSolver(ft, algo, avg_f64=True)
+    s = CFRSolver(ft, algo, avg_f64=True, persistent=persistent)
     n_iters = 40 if algo != "CFRPlus" else (150 if name == "NLLeduc_POT" else 60)
     curr, avg = [(0, s.exploitability_current())], []
     snaps = (1, 2, 3, 4, 5, 10, 11, 30, 31)
@@ -105,3 +106,15 @@ def test_cfr_plus_float32_average_within_tolerance():
         a = s.exploitability_average()
         ref = g["avg_series"][t - 1, 1]
         assert abs(a - ref) <= 1e-6 * abs(ref), (t, a, ref)
+
+
+def test_persistent_multi_iteration_launch_matches_golden():
+    """20 iterations inside ONE cooperative launch (bench cadence) land on the reference's iteration-20/40 numbers."""
+    from pokerrl_b200.solver import CFRSolver
+    ft = make_flat_tree("NLLeduc_POT")
+    g = golden("cfr_CFRPlus_NLLeduc_POT.npz")
+    s = CFRSolver(ft, "CFRPlus", avg_f64=True)
+    for t in (20, 40, 60):
+        s.iteration(20)
+        assert s.exploitability_current() == g["curr_series"][t, 1]
+        assert s.exploitability_average() == g["avg_series"][t - 1, 1]
