@@ -143,6 +143,30 @@ void prl_debug_set_timeline(void* device_u64_buffer);
 int prl_cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay, int avg_f64,
                   const int* strat_mode, int which, prl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * 7-card Hold'em hand evaluation (replaces lib_hand_eval.so; int32 strength, higher = better, identical encoding incl.
+ * the quads-kicker quirk - see oracle/hand_eval_oracle.c).  Cards are 1D ids c = rank*4 + suit.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* HoldemRules.get_hand_rank_all_hands_on_given_boards (game_rules.py:213-217) on device buffers:
+ * boards = DEVICE int8[n_boards][5], out = DEVICE int32[n_boards][1326] (-1 where the hand is blocked by the board;
+ * hand order = LUT_IDX_2_HOLE_CARDS). */
+int prl_hand_rank_boards(const int8_t* boards, int n_boards, int32_t* out, prl_stream_t stream);
+
+/* n independent 7-card hands: cards = DEVICE int8[n][7] -> out = DEVICE int32[n] (game_rules.py:219-223 batched). */
+int prl_hand_rank_7(const int8_t* cards, int n, int32_t* out, prl_stream_t stream);
+
+/* Legacy entry points with the exact native signatures the reference binds through ctypes (HOST arrays of row
+ * pointers, PokerRL/_/CppWrapper.py:24-27): CppHandeval.py:22-33 and CppLUT.py:22-35 can load this library unchanged.
+ * They stage through device memory and run the kernels above (synchronous). */
+int32_t get_hand_rank_52_holdem(int8_t** hand_2d /*[2][2]*/, int8_t** board_2d /*[5][2]*/);
+void get_hand_rank_all_hands_on_given_boards_52_holdem(int32_t** out /*[n][1326]*/, int8_t** boards_1d /*[n][5]*/,
+                                                       int32_t n, int8_t** idx2holecards, int8_t** card1d_to_2d);
+void get_hole_card_2_idx_lut(int16_t** lut /*[52][52]*/);
+void get_idx_2_hole_card_lut(int8_t** lut /*[1326][2]*/);
+int8_t get_1d_card(const int8_t* card_2d);
+void get_2d_card(int8_t card_1d, int8_t* out_card_2d);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,10 @@ def lib():
     for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration", "prl_cfr_sweep", "prl_pack_node_meta", "prl_cfr_iterations",
               "prl_evaluate"):
         getattr(L, f).restype = C.c_int
+    L.prl_hand_rank_boards.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.prl_hand_rank_7.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    for f in ("prl_hand_rank_boards", "prl_hand_rank_7"):
+        getattr(L, f).restype = C.c_int
     _lib = L
     return L
 

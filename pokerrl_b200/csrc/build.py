@@ -20,6 +20,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path
 SOURCES = {
     "prl_common.cu": [],
     "cfr_levels.cu": ["-fmad=false"],
+    "hand_eval.cu": [],
 }
 
 

@@ -1,0 +1,267 @@
+// 7-card Hold'em hand evaluation on the GPU + Hold'em index LUTs (integer work, bit-exact contract).
+//
+// Replaces the reference's binary-only natives (no source in the reference tree):
+//   lib_hand_eval.so  get_hand_rank_52_holdem / get_hand_rank_all_hands_on_given_boards_52_holdem
+//                     (PokerRL/game/_/cpp_wrappers/CppHandeval.py:19-65; callers game_rules.py:213-223, 296-306,
+//                      PokerEnv.py:533-535, LocalLBRWorker.py:420)
+//   lib_luts.so       get_hole_card_2_idx_lut / get_idx_2_hole_card_lut / get_1d_card / get_2d_card
+//                     (PokerRL/game/_/cpp_wrappers/CppLUT.py:14-94; look_up_table.py:95-134)
+// The int32 strength encoding (incl. the quads-kicker quirk) is documented in oracle/hand_eval_oracle.c, which is pinned
+// bit-for-bit against the reference binary; tests/test_gpu_hand_eval.py checks this file against both.
+//
+// Kernel shape: one block per board, the board's rank counts / suit masks are built once in registers by every thread
+// (5 cards), each thread then adds the two hole cards of its hands.  Pure ALU + 4 B store per hand: HBM-store bound at
+// scale (4 B out per 7-card evaluation).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pokerrl_b200.h"
+#include "prl_common.cuh"
+
+namespace {
+
+constexpr int kPairBase = 576011, kTwoPairBase = 658508, kTripsBase = 661446, kStraightBase = 664384,
+              kFlushBase = 664398, kFullHouseBase = 1240409, kQuadsBase = 1240618, kStraightFlushBase = 1240827;
+
+struct CardSet {
+    unsigned long long cnt;  // 4 bits per rank
+    unsigned suit[4];        // rank mask per suit
+    __host__ __device__ __forceinline__ void add(int c) {
+        const int r = c >> 2, s = c & 3;
+        cnt += 1ull << (4 * r);
+        suit[s] |= 1u << r;
+    }
+};
+
+__host__ __device__ __forceinline__ int straight_top(unsigned mask) {
+    // a run of five set bits ending at `top`; the wheel (A,2,3,4,5) has top = 3
+    unsigned m = mask & (mask >> 1) & (mask >> 2) & (mask >> 3) & (mask >> 4);  // bit i set: ranks i..i+4 present
+    if (m) {
+        int top = 0;
+        for (int i = 8; i >= 0; --i)
+            if (m & (1u << i)) { top = i + 4; break; }
+        return top;
+    }
+    return ((mask & 0x100Fu) == 0x100Fu) ? 3 : -1;
+}
+
+__host__ __device__ __forceinline__ int top5_value(unsigned mask) {
+    int v = 0, n = 0;
+    for (int r = 12; r >= 0 && n < 5; --r)
+        if (mask & (1u << r)) { v = v * 13 + r; ++n; }
+    return v;
+}
+
+__host__ __device__ __forceinline__ int popc13(unsigned m) {
+#ifdef __CUDA_ARCH__
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+
+// strength of the best 5-card hand in a 7-card set
+__host__ __device__ inline int rank_cardset(const CardSet& cs) {
+    const unsigned all = cs.suit[0] | cs.suit[1] | cs.suit[2] | cs.suit[3];
+    int flush_suit = -1;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        if (popc13(cs.suit[s]) >= 5) flush_suit = s;
+    if (flush_suit >= 0) {
+        const int st = straight_top(cs.suit[flush_suit]);
+        if (st >= 0) return kStraightFlushBase + st;
+    }
+    int quad = -1, trip1 = -1, trip2 = -1, pair1 = -1, pair2 = -1;
+    for (int r = 12; r >= 0; --r) {
+        const int n = (int)((cs.cnt >> (4 * r)) & 0xF);
+        if (n == 4) quad = r;
+        else if (n == 3) { if (trip1 < 0) trip1 = r; else if (trip2 < 0) trip2 = r; }
+        else if (n == 2) { if (pair1 < 0) pair1 = r; else if (pair2 < 0) pair2 = r; }
+    }
+    if (quad >= 0) {
+        // quirk of the reference binary: the kicker is the card right above the quads in descending order if there is
+        // one, otherwise the best card below
+        int k = -1;
+        for (int r = quad + 1; r <= 12 && k < 0; ++r)
+            if (all & (1u << r)) k = r;
+        for (int r = quad - 1; r >= 0 && k < 0; --r)
+            if (all & (1u << r)) k = r;
+        return kQuadsBase + 13 * quad + k;
+    }
+    if (trip1 >= 0 && (trip2 >= 0 || pair1 >= 0)) return kFullHouseBase + 13 * trip1 + (trip2 > pair1 ? trip2 : pair1);
+    if (flush_suit >= 0) return kFlushBase + top5_value(cs.suit[flush_suit]);
+    {
+        const int st = straight_top(all);
+        if (st >= 0) return kStraightBase + st;
+    }
+    if (trip1 >= 0) {
+        const unsigned rest = all & ~(1u << trip1);
+        int k0 = -1, k1 = -1;
+        for (int r = 12; r >= 0; --r)
+            if (rest & (1u << r)) { if (k0 < 0) k0 = r; else if (k1 < 0) k1 = r; }
+        return kTripsBase + 169 * trip1 + 13 * k0 + k1;
+    }
+    if (pair2 >= 0) {
+        const unsigned rest = all & ~((1u << pair1) | (1u << pair2));
+        int k = -1;
+        for (int r = 12; r >= 0 && k < 0; --r)
+            if (rest & (1u << r)) k = r;
+        return kTwoPairBase + 169 * pair1 + 13 * pair2 + k;
+    }
+    if (pair1 >= 0) {
+        const unsigned rest = all & ~(1u << pair1);
+        int k[3] = {0, 0, 0}, n = 0;
+        for (int r = 12; r >= 0 && n < 3; --r)
+            if (rest & (1u << r)) k[n++] = r;
+        return kPairBase + 2197 * pair1 + 169 * k[0] + 13 * k[1] + k[2];
+    }
+    return top5_value(all);
+}
+
+// hand index (LUT order: c1 < c2 lexicographic) -> c1, c2 without a table
+__host__ __device__ __forceinline__ void hole_cards_of(int idx, int& c1, int& c2) {
+    // rows: c1 = 0 has 51 hands, c1 = 1 has 50, ...; offset(c1) = c1 * (103 - c1) / 2
+    int a = (int)((103.0f - sqrtf(103.0f * 103.0f - 8.0f * (float)idx)) * 0.5f);
+    while (a * (103 - a) / 2 > idx) --a;
+    while ((a + 1) * (102 - a) / 2 <= idx) ++a;
+    c1 = a;
+    c2 = idx - a * (103 - a) / 2 + a + 1;
+}
+
+__global__ void rank_boards_kernel(const int8_t* __restrict__ boards, int n_boards, int32_t* __restrict__ out) {
+    const int b = blockIdx.x;
+    if (b >= n_boards) return;
+    CardSet base = {0ull, {0u, 0u, 0u, 0u}};
+    unsigned long long bmask = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int c = boards[b * 5 + i];
+        base.add(c);
+        bmask |= 1ull << c;
+    }
+    for (int idx = threadIdx.x; idx < 1326; idx += blockDim.x) {
+        int c1, c2;
+        hole_cards_of(idx, c1, c2);
+        int v = -1;
+        if (!((bmask >> c1) & 1ull) && !((bmask >> c2) & 1ull)) {
+            CardSet cs = base;
+            cs.add(c1);
+            cs.add(c2);
+            v = rank_cardset(cs);
+        }
+        out[(size_t)b * 1326 + idx] = v;
+    }
+}
+
+__global__ void rank7_kernel(const int8_t* __restrict__ cards, int n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CardSet cs = {0ull, {0u, 0u, 0u, 0u}};
+#pragma unroll
+    for (int j = 0; j < 7; ++j) cs.add(cards[(size_t)i * 7 + j]);
+    out[i] = rank_cardset(cs);
+}
+
+}  // namespace
+
+extern "C" int prl_hand_rank_boards(const int8_t* boards, int n_boards, int32_t* out, prl_stream_t stream) {
+    if (n_boards <= 0) return 0;
+    rank_boards_kernel<<<n_boards, 256, 0, (cudaStream_t)stream>>>(boards, n_boards, out);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_hand_rank_boards");
+}
+
+extern "C" int prl_hand_rank_7(const int8_t* cards, int n, int32_t* out, prl_stream_t stream) {
+    if (n <= 0) return 0;
+    rank7_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cards, n, out);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_hand_rank_7");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Legacy entry points with the EXACT signatures of the reference's natives (arrays of row pointers, host memory;
+// PokerRL/_/CppWrapper.py:24-27), so that CppHandeval / CppLibHoldemLuts can bind this library unchanged.  They stage
+// through device memory and run the kernels above - there is no host evaluator in this library.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+int stage_and_rank_boards(int32_t** out, int8_t** boards, int n) {
+    if (n <= 0) return 0;
+    int8_t* d_b = nullptr;
+    int32_t* d_o = nullptr;
+    int8_t* h_b = (int8_t*)malloc((size_t)n * 5);
+    int32_t* h_o = (int32_t*)malloc((size_t)n * 1326 * sizeof(int32_t));
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < 5; ++j) h_b[i * 5 + j] = boards[i][j];
+    cudaError_t e = cudaMalloc(&d_b, (size_t)n * 5);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, (size_t)n * 1326 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_b, h_b, (size_t)n * 5, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rank_boards_kernel<<<n, 256>>>(d_b, n, d_o);
+        prl::count_launch();
+        e = cudaMemcpy(h_o, d_o, (size_t)n * 1326 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess)
+        for (int i = 0; i < n; ++i) memcpy(out[i], h_o + (size_t)i * 1326, 1326 * sizeof(int32_t));
+    cudaFree(d_b);
+    cudaFree(d_o);
+    free(h_b);
+    free(h_o);
+    return prl::check(e, "get_hand_rank_all_hands_on_given_boards_52_holdem");
+}
+}  // namespace
+
+// CppHandeval.py:45-65.  idx2holecards / card1d_to_2d are accepted for signature compatibility; the index order they
+// describe is the fixed LUT order this library implements.
+extern "C" void get_hand_rank_all_hands_on_given_boards_52_holdem(int32_t** out, int8_t** boards_1d, int32_t n,
+                                                                  int8_t** idx2holecards, int8_t** card1d_to_2d) {
+    (void)idx2holecards;
+    (void)card1d_to_2d;
+    stage_and_rank_boards(out, boards_1d, n);
+}
+
+// CppHandeval.py:34-43: hand_2d[2][2], board_2d[5][2] as (rank, suit) rows
+extern "C" int32_t get_hand_rank_52_holdem(int8_t** hand_2d, int8_t** board_2d) {
+    int8_t h[7];
+    for (int i = 0; i < 2; ++i) h[i] = (int8_t)(hand_2d[i][0] * 4 + hand_2d[i][1]);
+    for (int i = 0; i < 5; ++i) h[2 + i] = (int8_t)(board_2d[i][0] * 4 + board_2d[i][1]);
+    int8_t* d_c = nullptr;
+    int32_t* d_o = nullptr;
+    int32_t v = -1;
+    cudaError_t e = cudaMalloc(&d_c, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_c, h, 7, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rank7_kernel<<<1, 32>>>(d_c, 1, d_o);
+        prl::count_launch();
+        e = cudaMemcpy(&v, d_o, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_c);
+    cudaFree(d_o);
+    prl::check(e, "get_hand_rank_52_holdem");
+    return v;
+}
+
+// ---- lib_luts.so equivalents (CppLUT.py:22-35, 73-94): pure index arithmetic, filled into caller-owned tables ----------
+extern "C" void get_hole_card_2_idx_lut(int16_t** lut /*[52][52]*/) {
+    int idx = 0;
+    for (int c1 = 0; c1 < 52; ++c1)
+        for (int c2 = c1 + 1; c2 < 52; ++c2) lut[c1][c2] = (int16_t)idx++;
+}
+
+extern "C" void get_idx_2_hole_card_lut(int8_t** lut /*[1326][2]*/) {
+    int idx = 0;
+    for (int c1 = 0; c1 < 52; ++c1)
+        for (int c2 = c1 + 1; c2 < 52; ++c2, ++idx) {
+            lut[idx][0] = (int8_t)c1;
+            lut[idx][1] = (int8_t)c2;
+        }
+}
+
+extern "C" int8_t get_1d_card(const int8_t* card_2d) { return (int8_t)(card_2d[0] * 4 + card_2d[1]); }
+
+extern "C" void get_2d_card(int8_t card_1d, int8_t* out) {
+    out[0] = (int8_t)(card_1d / 4);
+    out[1] = (int8_t)(card_1d % 4);
+}

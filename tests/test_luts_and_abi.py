@@ -1,0 +1,70 @@
+"""CPU-side tests: LUT tables against the reference's, the hand-eval oracle against the golden ranks, and that the
+C-ABI library loads and exports every symbol include/pokerrl_b200.h declares (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import golden
+from pokerrl_b200.game import games
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name,game", [("holdem", games.DiscretizedNLHoldem), ("leduc", games.DiscretizedNLLeduc)])
+def test_luts_match_reference(name, game):
+    g = golden("luts.npz")
+    L = game.get_lut_holder()
+    for k in ("LUT_1DCARD_2_2DCARD", "LUT_2DCARD_2_1DCARD", "LUT_IDX_2_HOLE_CARDS", "LUT_HOLE_CARDS_2_IDX",
+              "LUT_CARD_IN_WHAT_RANGE_IDXS", "LUT_RANGE_IDX_TO_PRIVATE_OBS"):
+        ref = g["%s_%s" % (name, k)]
+        mine = getattr(L, k)
+        assert np.array_equal(mine, ref), k
+        if name == "holdem":
+            assert mine.dtype == ref.dtype, (k, mine.dtype, ref.dtype)  # test_look_up_table.py:16-56 pins dtypes
+    for k in ("DICT_LUT_N_BOARDS", "DICT_LUT_N_CARDS_OUT", "DICT_LUT_CARDS_DEALT_IN_TRANSITION_TO",
+              "DICT_LUT_N_BOARD_BRANCHES"):
+        ref = {int(a): int(b) for a, b in g["%s_%s" % (name, k)]}
+        mine = getattr(L, k)
+        for kk, vv in ref.items():
+            if kk in game.RULES.ALL_ROUNDS_LIST or k in ("DICT_LUT_N_CARDS_OUT", "DICT_LUT_CARDS_DEALT_IN_TRANSITION_TO"):
+                assert mine[kk] == vv, (k, kk)
+
+
+def test_lut_accessors_reference_tests():
+    """value checks of the reference's own test_look_up_table.py:110-167"""
+    L = games.DiscretizedNLHoldem.get_lut_holder()
+    assert L.get_1d_card(np.array([0, 3], np.int8)) == 3 and L.get_1d_card(np.array([12, 3], np.int8)) == 51
+    n = 0
+    for c1 in range(52):
+        for c2 in range(c1 + 1, 52):
+            assert L.LUT_HOLE_CARDS_2_IDX[c1, c2] == n
+            n += 1
+    assert np.array_equal(L.get_2d_cards(np.array([5, -127], np.int8)), np.array([[1, 1], [-127, -127]], np.int8))
+    assert L.get_range_idx_from_hole_cards(np.array([[12, 3], [0, 0]], np.int8)) == L.LUT_HOLE_CARDS_2_IDX[0, 51]
+
+
+def test_hand_eval_oracle_matches_reference_binary_fixture():
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    orc = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libhand_eval_oracle.so"))
+    orc.orc_rank_boards.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    g = golden("hand_ranks.npz")
+    boards = np.ascontiguousarray(g["boards"])
+    out = np.zeros((len(boards), 1326), np.int32)
+    orc.orc_rank_boards(out.ctypes.data, boards.ctypes.data, len(boards))
+    assert np.array_equal(out, g["ranks"])
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from pokerrl_b200 import _native
+    L = _native.lib()
+    hdr = open(os.path.join(ROOT, "include", "pokerrl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = re.findall(r"\b((?:prl_|get_)[a-z0-9_]+)\s*\(", hdr)
+    assert len(names) >= 15
+    for n in sorted(set(names)):
+        assert hasattr(L, n), n
+    assert L.prl_abi_version() >= 1
