@@ -75,6 +75,22 @@ typedef struct {
     const void* meta;            /* DEVICE 16-byte record per node, filled by prl_pack_node_meta() from the arrays above:
                                     {first_child, first_slot, pot, kind | acted_last | board | n_children}; the sweeps
                                     read node structure only through it (one 128-bit load per node) */
+    /* ---- two-hole-card games only (n_hole == 2); NULL / 0 otherwise ------------------------------------------- */
+    const int64_t* level_ndec;   /* HOST int64[n_levels]: decision nodes per level (first in `order`, then chance nodes) */
+    const int8_t* hand_cards;    /* DEVICE int8[n_range][2]: LUT_IDX_2_HOLE_CARDS */
+    int32_t n_boards;            /* rows of the board tables below; node.board indexes them */
+    int32_t max_chance_children; /* largest fan-out of a chance node */
+    const uint64_t* board_mask;  /* DEVICE uint64[n_boards]: bit c set iff card c lies on the board */
+    const float* board_prob;     /* DEVICE float[n_boards]: factor applied to BOTH reach rows when this board is dealt
+                                    (1 / C(deck - 4, k) in the full game; hands holding a board card get 0) */
+    const float* board_mult;     /* DEVICE float[n_boards]: weight of this board's values in its parent's sum (1, or
+                                    orbit size / n_sym for a suit-isomorphism class representative) */
+    const int16_t* board_gs;     /* DEVICE int16[n_boards][n_range]: # live hands strictly weaker (-1: hand blocked)   */
+    const int16_t* board_ge;     /* DEVICE int16[n_boards][n_range]: # live hands weaker or equal                      */
+    const int16_t* board_pos;    /* DEVICE int16[n_boards][n_range]: position in strength order (prl_board_order_tables) */
+    int32_t n_sym;               /* hand permutations summed at chance parents (24 suit permutations with isomorphism, else 0/1) */
+    const int16_t* sym_perm;     /* DEVICE int16[n_sym][n_range] */
+    float eq_const;              /* opponent-hand normaliser C(deck,2)/C(deck-2,2) (ValueFiller.py:19 generalised) */
 } prl_tree_t;
 
 /* Caller-owned work buffers. */
@@ -85,6 +101,8 @@ typedef struct {
     float* regret; /* DEVICE float[n_slots][ld]      node.data["regret"] */
     float* strat;  /* DEVICE float[n_slots][ld]      node.strategy */
     void* avg;     /* DEVICE float|double[n_slots][ld]  node.data["avg_strat"] (CFR+) / ["avg_strat_sum"] */
+    void* workspace;          /* DEVICE scratch for the chance-node reductions of two-card games (else NULL) */
+    uint64_t workspace_bytes; /* >= 4 * n_chance_per_level * (ceil(max_chance_children / 128) + 1) * ld * 4 bytes */
 } prl_buffers_t;
 
 /* library info */
@@ -142,6 +160,11 @@ void prl_debug_set_timeline(void* device_u64_buffer);
  * reach/average sweep); prl_cfr_half_iteration == which 3.  Used to time the sweeps individually. */
 int prl_cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay, int avg_f64,
                   const int* strat_mode, int which, prl_stream_t stream);
+
+/* Strength-order tables of complete boards for the two-card showdown rows: ranks = DEVICE int32[n_boards][n_range]
+ * (prl_hand_rank_boards; -1 = blocked) -> gs / ge / pos = DEVICE int16[n_boards][n_range] (see prl_tree_t). */
+int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_range, int16_t* gs, int16_t* ge, int16_t* pos,
+                           prl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * 7-card Hold'em hand evaluation (replaces lib_hand_eval.so; int32 strength, higher = better, identical encoding incl.

@@ -24,12 +24,17 @@ class PrlTree(C.Structure):
         ("parent", C.c_void_p), ("first_child", C.c_void_p), ("n_children", C.c_void_p), ("slot", C.c_void_p),
         ("kind", C.c_void_p), ("acted_last", C.c_void_p), ("pot", C.c_void_p), ("board", C.c_void_p),
         ("order", C.c_void_p), ("level_nonterm", C.c_void_p), ("meta", C.c_void_p),
+        ("level_ndec", C.c_void_p), ("hand_cards", C.c_void_p), ("n_boards", C.c_int32),
+        ("max_chance_children", C.c_int32), ("board_mask", C.c_void_p), ("board_prob", C.c_void_p),
+        ("board_mult", C.c_void_p), ("board_gs", C.c_void_p), ("board_ge", C.c_void_p), ("board_pos", C.c_void_p),
+        ("n_sym", C.c_int32), ("sym_perm", C.c_void_p), ("eq_const", C.c_float),
     ]
 
 
 class PrlBuffers(C.Structure):
     _fields_ = [("reach", C.c_void_p), ("ev", C.c_void_p), ("ev_br", C.c_void_p), ("regret", C.c_void_p),
-                ("strat", C.c_void_p), ("avg", C.c_void_p)]
+                ("strat", C.c_void_p), ("avg", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_uint64)]
 
 
 _lib = None
@@ -60,6 +65,8 @@ def lib():
     for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration", "prl_cfr_sweep", "prl_pack_node_meta", "prl_cfr_iterations",
               "prl_evaluate"):
         getattr(L, f).restype = C.c_int
+    L.prl_board_order_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.prl_board_order_tables.restype = C.c_int
     L.prl_hand_rank_boards.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.prl_hand_rank_7.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     for f in ("prl_hand_rank_boards", "prl_hand_rank_7"):

@@ -21,6 +21,7 @@ SOURCES = {
     "prl_common.cu": [],
     "cfr_levels.cu": ["-fmad=false"],
     "hand_eval.cu": [],
+    "cfr_twocard.cu": [],
 }
 
 

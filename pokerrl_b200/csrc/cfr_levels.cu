@@ -29,6 +29,15 @@
 
 namespace cg = cooperative_groups;
 
+// two-hole-card sweeps (cfr_twocard.cu)
+namespace prl2 {
+int reach_pass(const prl_tree_t*, const prl_buffers_t*, int player_mask, const int* mode, cudaStream_t);
+int value_pass(const prl_tree_t*, const prl_buffers_t*, int player_mask, int with_br, const int* mode, cudaStream_t);
+int root_exploitability(const prl_tree_t*, const prl_buffers_t*, float* out, cudaStream_t);
+int cfr_sweep(const prl_tree_t*, const prl_buffers_t*, int algo, int p, int iter, int delay, const int* mode, int which,
+              cudaStream_t);
+}  // namespace prl2
+
 namespace {
 
 constexpr int kThreads = 128;
@@ -608,6 +617,7 @@ extern "C" int prl_pack_node_meta(const prl_tree_t* tree, void* out_meta, prl_st
 
 extern "C" int prl_reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, const int* strat_mode,
                               prl_stream_t stream) {
+    if (tree && tree->n_hole == 2) return prl2::reach_pass(tree, buf, player_mask, strat_mode, (cudaStream_t)stream);
     if (int e = check_tree(tree)) return e;
     Ctx c{*tree, *buf, 0, 0, player_mask, {strat_mode[0], strat_mode[1]}, 0, -1, 0, 0, 0};
     reach_sweep(c, false, (cudaStream_t)stream);
@@ -616,8 +626,9 @@ extern "C" int prl_reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, 
 
 extern "C" int prl_value_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int with_br,
                               const int* strat_mode, prl_stream_t stream) {
-    if (int e = check_tree(tree)) return e;
     if (with_br && !buf->ev_br) return prl::fail("prl_value_pass: with_br needs ev_br");
+    if (tree && tree->n_hole == 2) return prl2::value_pass(tree, buf, player_mask, with_br, strat_mode, (cudaStream_t)stream);
+    if (int e = check_tree(tree)) return e;
     Ctx c{*tree, *buf, 0, 0, player_mask, {strat_mode[0], strat_mode[1]}, 0, -1, 0, 0, 0};
     value_sweep(c, with_br != 0, false, (cudaStream_t)stream);
     return prl::check(cudaGetLastError(), "prl_value_pass");
@@ -626,6 +637,7 @@ extern "C" int prl_value_pass(const prl_tree_t* tree, const prl_buffers_t* buf, 
 extern "C" int prl_root_exploitability(const prl_tree_t* tree, const prl_buffers_t* buf, float* out_expl,
                                        prl_stream_t stream) {
     if (!buf->ev_br) return prl::fail("prl_root_exploitability needs ev_br");
+    if (tree->n_hole == 2) return prl2::root_exploitability(tree, buf, out_expl, (cudaStream_t)stream);
     root_exploitability_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*tree, *buf, out_expl);
     prl::count_launch();
     return prl::check(cudaGetLastError(), "prl_root_exploitability");
@@ -633,6 +645,10 @@ extern "C" int prl_root_exploitability(const prl_tree_t* tree, const prl_buffers
 
 extern "C" int prl_cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
                              int avg_f64, const int* strat_mode, int which, prl_stream_t stream) {
+    if (tree && tree->n_hole == 2) {
+        if (avg_f64) return prl::fail("two-card games keep the average in float32");
+        return prl2::cfr_sweep(tree, buf, algo, p, iter, delay, strat_mode, which, (cudaStream_t)stream);
+    }
     if (int e = check_tree(tree)) return e;
     if (p < 0 || p > 1 || algo < 0 || algo > 2) return prl::fail("prl_cfr_sweep: bad p / algo");
     if (algo != PRL_ALGO_CFR_PLUS && avg_f64) return prl::fail("avg_f64 only applies to CFR+");
@@ -701,6 +717,16 @@ extern "C" void prl_debug_set_timeline(void* device_u64_buffer) { g_timeline = (
 
 extern "C" int prl_cfr_iterations(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int iter0, int n_iters,
                                   int delay, int avg_f64, const int* strat_mode, prl_stream_t stream) {
+    if (tree && tree->n_hole == 2) {  // the big trees of the two-card games are bandwidth-bound: plain per-level launches
+        if (avg_f64) return prl::fail("two-card games keep the average in float32");
+        int mode[2] = {strat_mode[0], strat_mode[1]};
+        for (int it = 0; it < n_iters; ++it)
+            for (int p = 0; p < 2; ++p) {
+                if (int e = prl2::cfr_sweep(tree, buf, algo, p, iter0 + it, delay, mode, 3, (cudaStream_t)stream)) return e;
+                mode[p] = PRL_STRAT_F32;
+            }
+        return 0;
+    }
     if (int e = check_tree(tree)) return e;
     if (algo < 0 || algo > 2 || n_iters < 0) return prl::fail("prl_cfr_iterations: bad algo / n_iters");
     if (algo != PRL_ALGO_CFR_PLUS && avg_f64) return prl::fail("avg_f64 only applies to CFR+");
@@ -714,8 +740,14 @@ extern "C" int prl_cfr_iterations(const prl_tree_t* tree, const prl_buffers_t* b
 
 extern "C" int prl_evaluate(const prl_tree_t* tree, const prl_buffers_t* buf, const int* strat_mode, int do_reach,
                             float* out_expl, prl_stream_t stream) {
-    if (int e = check_tree(tree)) return e;
     if (!buf->ev_br || !out_expl) return prl::fail("prl_evaluate needs ev_br and out_expl");
+    if (tree && tree->n_hole == 2) {
+        if (do_reach)
+            if (int e = prl2::reach_pass(tree, buf, 3, strat_mode, (cudaStream_t)stream)) return e;
+        if (int e = prl2::value_pass(tree, buf, 3, 1, strat_mode, (cudaStream_t)stream)) return e;
+        return prl2::root_exploitability(tree, buf, out_expl, (cudaStream_t)stream);
+    }
+    if (int e = check_tree(tree)) return e;
     Ctx c{*tree, *buf, 0, 0, 3, {strat_mode[0], strat_mode[1]}, 0, -1, 0, 0, 0};
     Levels lv;
     if (int e = make_levels(tree, &lv)) return e;

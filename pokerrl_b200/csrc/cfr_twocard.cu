@@ -1,0 +1,546 @@
+// Level-synchronous public-tree sweeps for TWO-HOLE-CARD games (Hold'em family, range R = C(deck,2) = 1326) - sm_100a.
+//
+// The reference has no working value path for these games (ValueFiller.py:18-19 and PublicTree.py:193-203 are
+// one-card only); the arithmetic here is the generalisation stated in SURVEY.md appendix A and restated in float64 by
+// oracle/cfr2_numpy.py: blocker-aware fold / showdown values, board deals that zero blocked hands, board-weighted chance
+// sums with optional suit-isomorphism symmetrisation.  Everything else (regrets, regret matching, averaging, BR) is the
+// same statement as the one-card sweeps (cfr_levels.cu), evaluated in float32.
+//
+// Mapping: one THREAD per (node, hand) with hands contiguous -> every row access is a fully coalesced 5.3 KB stream;
+// node structure loads are warp-uniform (broadcast).  Terminal rows are evaluated by one CTA per terminal node:
+//   fold      T - cs[c1] - cs[c2] + r[h]                 (52 per-card sums, deterministic)
+//   showdown  O(R) via the board's strength order: scatter by sorted position, block scan, strictly-weaker /
+//             strictly-stronger mass from group boundaries, minus a ~100-term blocker correction per hand
+// instead of the O(R^2) sign-matrix product: these rows are HBM-bound, the dense 1326x1326 contraction (tensor cores)
+// would only add work - see DESIGN.md §6.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pokerrl_b200.h"
+#include "prl_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTermThreads = 512;
+constexpr int kChanceChunk = 128;  // children summed per block in the first stage of a chance-node reduction
+
+struct Ctx2 {
+    prl_tree_t T;
+    prl_buffers_t B;
+    int lo, n;       // first work-list entry of this launch, number of entries
+    int mask;        // seats to process
+    int mode[2];     // strategy source per seat
+    int algo, upd_p, iter, delay;
+};
+
+__device__ __forceinline__ const float* strat_table(const Ctx2& c, int m) {
+    return (m == PRL_STRAT_F32) ? c.B.strat : (const float*)c.B.avg;
+}
+
+// probability of the action leading to the child in row `slot` (rows fs..fs+A-1 belong to one decision node)
+__device__ __forceinline__ float strat_value(const Ctx2& c, int m, int slot, int fs, int A, int h) {
+    const size_t ld = c.T.ld;
+    if (m == PRL_STRAT_UNIFORM64) return 1.0f / (float)A;
+    if (m == PRL_STRAT_AVG_SUM) {  // reach-weighted sums, normalised on the fly (LinearCFR.py:64-71)
+        const float* tab = (const float*)c.B.avg;
+        float tot = 0.0f;
+        for (int j = 0; j < A; ++j) tot += tab[(size_t)(fs + j) * ld + h];
+        return (tot == 0.0f) ? 1.0f / (float)A : tab[(size_t)slot * ld + h] / tot;
+    }
+    return strat_table(c, m)[(size_t)slot * ld + h];
+}
+
+__device__ __forceinline__ bool hand_blocked(const prl_tree_t& T, int h, unsigned long long bmask) {
+    const int c1 = T.hand_cards[2 * h], c2 = T.hand_cards[2 * h + 1];
+    return ((bmask >> c1) | (bmask >> c2)) & 1ull;
+}
+
+// ------------------------------------------------------------------------------------------------ reach (top-down)
+// thread = (child node n of the level, hand h); StrategyFiller.py:118-146 generalised
+template <bool UPDATE_AVG>
+__global__ void __launch_bounds__(kThreads) reach2_kernel(const Ctx2 c) {
+    const int ld = c.T.ld;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = c.lo + (int)(idx / ld);
+    const int h = (int)(idx % ld);
+    if (n >= c.lo + c.n || h >= c.T.n_range) return;
+    const size_t N = (size_t)c.T.n_nodes;
+    const int par = c.T.parent[n];
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {
+        if (!(c.mask & (1 << q))) continue;
+        float* reach_q = c.B.reach + (size_t)q * N * ld;
+        float r;
+        if (par < 0) {
+            r = 1.0f / (float)c.T.n_range;  // PublicTree.py:122-124
+        } else {
+            const float rp = reach_q[(size_t)par * ld + h];
+            const int pk = c.T.kind[par];
+            if (pk == PRL_KIND_CHANCE) {  // the deal multiplies both rows and zeroes hands holding a board card
+                const int b = c.T.board[n];
+                r = hand_blocked(c.T, h, c.T.board_mask[b]) ? 0.0f : rp * c.T.board_prob[b];
+            } else if (pk == q) {
+                const int slot = c.T.slot[n];
+                const int m = c.mode[q];
+                const int fs = c.T.slot[c.T.first_child[par]];
+                const float s = strat_value(c, m, slot, fs, c.T.n_children[par], h);
+                r = s * rp;
+                if (UPDATE_AVG && q == c.upd_p) {
+                    float* a = (float*)c.B.avg + (size_t)slot * ld + h;
+                    if (c.algo == PRL_ALGO_CFR_PLUS) {  // CFRPlus.py:65-87 (float table)
+                        if (c.iter >= c.delay) {
+                            const double cw = 0.5 * ((double)c.iter * (c.iter + 1) - (double)c.delay * (c.delay + 1));
+                            const double nw = (double)c.iter - c.delay + 1;
+                            *a = (float)(cw / (cw + nw)) * (*a) + (float)(nw / (cw + nw)) * s;
+                        }
+                    } else if (c.algo == PRL_ALGO_LINEAR) {
+                        *a = *a + r * (float)(c.iter + 1);  // LinearCFR.py:56-61
+                    } else {
+                        *a = *a + r;  // VanillaCFR.py:57-62
+                    }
+                }
+            } else {
+                r = rp;
+            }
+        }
+        reach_q[(size_t)n * ld + h] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ decision nodes (bottom-up)
+// thread = (work-list entry t -> decision node n, hand h); ValueFiller.py:80-93 + _CFRBase.py:146-185 + regret matching
+template <bool WITH_BR, bool UPDATE>
+__global__ void __launch_bounds__(kThreads) value2_kernel(const Ctx2 c) {
+    const int ld = c.T.ld;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (int)(idx / ld);
+    const int h = (int)(idx % ld);
+    if (t >= c.n || h >= c.T.n_range) return;
+    const int n = c.T.order[c.lo + t];
+    const size_t N = (size_t)c.T.n_nodes;
+    const int kind = c.T.kind[n], fc = c.T.first_child[n], A = c.T.n_children[n];
+    const int fs = c.T.slot[fc];
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        if (!(c.mask & (1 << p))) continue;
+        float* ev_p = c.B.ev + (size_t)p * N * ld;
+        float* evbr_p = WITH_BR ? c.B.ev_br + (size_t)p * N * ld : nullptr;
+        const float* ecol = ev_p + (size_t)fc * ld + h;
+        float v = 0.0f, vbr = 0.0f;
+        if (kind != p) {  // the other seat acts: sums over children
+            for (int k = 0; k < A; ++k) v += ecol[(size_t)k * ld];
+            if (WITH_BR)
+                for (int k = 0; k < A; ++k) vbr += evbr_p[(size_t)(fc + k) * ld + h];
+        } else {
+            const int m = c.mode[p];
+            for (int k = 0; k < A; ++k) v += strat_value(c, m, fs + k, fs, A, h) * ecol[(size_t)k * ld];
+            if (WITH_BR) {
+                vbr = evbr_p[(size_t)fc * ld + h];
+                for (int k = 1; k < A; ++k) vbr = fmaxf(vbr, evbr_p[(size_t)(fc + k) * ld + h]);
+            }
+            if (UPDATE && p == c.upd_p) {
+                float* rcol = c.B.regret + (size_t)fs * ld + h;
+                float* scol = c.B.strat + (size_t)fs * ld + h;
+                const float w = (float)(c.iter + 1);
+                float ssum = 0.0f;
+                for (int k = 0; k < A; ++k) {
+                    const float d = ecol[(size_t)k * ld] - v;
+                    float r;
+                    if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rcol[(size_t)k * ld], 0.0f);
+                    else if (c.algo == PRL_ALGO_LINEAR) r = w * d + rcol[(size_t)k * ld];
+                    else r = d + rcol[(size_t)k * ld];
+                    rcol[(size_t)k * ld] = r;
+                    ssum += fmaxf(r, 0.0f);
+                }
+                const float uni = 1.0f / (float)A;
+                const float inv = (ssum > 0.0f) ? 1.0f / ssum : 0.0f;
+                for (int k = 0; k < A; ++k)
+                    scol[(size_t)k * ld] = (ssum > 0.0f) ? fmaxf(rcol[(size_t)k * ld], 0.0f) * inv : uni;
+            }
+        }
+        ev_p[(size_t)n * ld + h] = v;
+        if (WITH_BR) evbr_p[(size_t)n * ld + h] = vbr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ chance nodes (bottom-up)
+// stage 1: block (chance entry j, chunk) sums board_mult * child rows of its chunk -> workspace[arr][j][chunk][h]
+// stage 2: thread (j, h): sums the chunks in order -> workspace W[arr][j][h]
+// stage 3: thread (j, h): ev[n][h] = sum over suit permutations of W (or W itself) - DESIGN.md §6
+// arr = 2 * seat + (0: ev, 1: ev_br)
+struct ChanceGeom {
+    int n_chance, max_chunks;
+    size_t w_off;  // float offset of the W vectors inside the workspace
+};
+
+__device__ __forceinline__ const float* node_array(const Ctx2& c, int arr) {
+    const size_t stride = (size_t)c.T.n_nodes * c.T.ld;
+    return ((arr & 1) ? c.B.ev_br : c.B.ev) + (size_t)(arr >> 1) * stride;
+}
+
+__global__ void __launch_bounds__(kThreads) chance_partial_kernel(const Ctx2 c, const ChanceGeom g, const int n_arr_mask) {
+    const int j = blockIdx.x / g.max_chunks, chunk = blockIdx.x % g.max_chunks;
+    const int n = c.T.order[c.lo + j];
+    const int fc = c.T.first_child[n], A = c.T.n_children[n];
+    const int k0 = chunk * kChanceChunk, k1 = min(A, k0 + kChanceChunk);
+    if (k0 >= A) return;
+    const int ld = c.T.ld;
+    float* ws = (float*)c.B.workspace;
+    for (int arr = 0; arr < 4; ++arr) {
+        if (!(n_arr_mask & (1 << arr))) continue;
+        const float* src = node_array(c, arr);
+        float* dst = ws + (((size_t)arr * g.n_chance + j) * g.max_chunks + chunk) * ld;
+        for (int h = threadIdx.x; h < c.T.n_range; h += blockDim.x) {
+            float acc = 0.0f;
+            for (int k = k0; k < k1; ++k) acc += c.T.board_mult[c.T.board[fc + k]] * src[(size_t)(fc + k) * ld + h];
+            dst[h] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) chance_sum_kernel(const Ctx2 c, const ChanceGeom g, const int n_arr_mask) {
+    const int ld = c.T.ld;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(idx / ld), h = (int)(idx % ld);
+    if (j >= g.n_chance || h >= c.T.n_range) return;
+    const int n = c.T.order[c.lo + j];
+    const int chunks = (c.T.n_children[n] + kChanceChunk - 1) / kChanceChunk;
+    float* ws = (float*)c.B.workspace;
+    for (int arr = 0; arr < 4; ++arr) {
+        if (!(n_arr_mask & (1 << arr))) continue;
+        const float* src = ws + (((size_t)arr * g.n_chance + j) * g.max_chunks) * ld + h;
+        float acc = 0.0f;
+        for (int k = 0; k < chunks; ++k) acc += src[(size_t)k * ld];
+        ws[g.w_off + ((size_t)arr * g.n_chance + j) * ld + h] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) chance_final_kernel(const Ctx2 c, const ChanceGeom g, const int n_arr_mask) {
+    const int ld = c.T.ld;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(idx / ld), h = (int)(idx % ld);
+    if (j >= g.n_chance || h >= c.T.n_range) return;
+    const int n = c.T.order[c.lo + j];
+    const float* ws = (const float*)c.B.workspace;
+    for (int arr = 0; arr < 4; ++arr) {
+        if (!(n_arr_mask & (1 << arr))) continue;
+        const float* W = ws + g.w_off + ((size_t)arr * g.n_chance + j) * ld;
+        float v;
+        if (c.T.n_sym > 1) {
+            v = 0.0f;
+            for (int s = 0; s < c.T.n_sym; ++s) v += W[c.T.sym_perm[(size_t)s * c.T.n_range + h]];
+        } else {
+            v = W[h];
+        }
+        const_cast<float*>(node_array(c, arr))[(size_t)n * ld + h] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ terminals (bottom-up)
+// hand index of the unordered pair (a, b), a != b, in LUT order (c1 < c2 lexicographic)
+__device__ __forceinline__ int pair_index(int a, int b, int n_deck) {
+    const int c1 = min(a, b), c2 = max(a, b);
+    return c1 * (2 * n_deck - 1 - c1) / 2 + (c2 - c1 - 1);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red /* >= 32 floats */) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < (blockDim.x >> 5)) ? red[l] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;  // every thread holds the total (fixed reduction order: deterministic)
+}
+
+// one CTA per terminal node; ValueFiller.py:34-62, 103-158 generalised
+template <bool WITH_BR>
+__global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
+    extern __shared__ float smem[];
+    const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck;
+    float* ro = smem;                      // [R]      opponent reach row
+    float* srt = ro + R;                   // [R + 1]  reach in strength order, then its exclusive prefix sums
+    float* cs = srt + R + 1;               // [64]     per-card sums
+    float* red = cs + 64;                  // [32]
+    float* wsum = red + 32;                // [kTermThreads / 32 + 1]
+    const int n = c.T.order[c.lo + blockIdx.x];
+    const int kind = c.T.kind[n];
+    const int b = c.T.board[n];
+    const size_t N = (size_t)c.T.n_nodes;
+    const float K = c.T.eq_const;
+    const float half_pot = c.T.pot[n];
+    const unsigned long long bmask = (b >= 0) ? c.T.board_mask[b] : 0ull;
+    const int16_t* gs_tab = (b >= 0 && c.T.board_gs) ? c.T.board_gs + (size_t)b * R : nullptr;
+    const int16_t* ge_tab = (b >= 0 && c.T.board_ge) ? c.T.board_ge + (size_t)b * R : nullptr;
+    const int16_t* pos_tab = (b >= 0 && c.T.board_pos) ? c.T.board_pos + (size_t)b * R : nullptr;
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        if (!(c.mask & (1 << p))) continue;
+        __syncthreads();
+        const float* ro_g = c.B.reach + ((size_t)(1 - p) * N + n) * ld;
+        float part = 0.0f;
+        for (int h = threadIdx.x; h < R; h += blockDim.x) {
+            const float r = ro_g[h];
+            ro[h] = r;
+            part += r;
+        }
+        const float T = block_sum(part, red);  // includes the barrier that publishes ro[]
+        float* ev_p = c.B.ev + ((size_t)p * N + n) * ld;
+        float* evbr_p = WITH_BR ? c.B.ev_br + ((size_t)p * N + n) * ld : nullptr;
+        if (kind == PRL_KIND_FOLD) {
+            // per-card sums cs[x] = sum of ro over the hands containing card x (each of the first n_deck threads: one card)
+            if (threadIdx.x < n_deck) {
+                const int x = threadIdx.x;
+                float s = 0.0f;
+                for (int y = 0; y < n_deck; ++y)
+                    if (y != x) s += ro[pair_index(x, y, n_deck)];
+                cs[x] = s;
+            }
+            __syncthreads();
+            const float sgn = (c.T.acted_last[n] == p) ? -1.0f : 1.0f;
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
+                float e = (T - cs[c1] - cs[c2] + ro[h]) * sgn * K;
+                if (((bmask >> c1) | (bmask >> c2)) & 1ull) e = 0.0f;
+                const float v = e * half_pot * 0.5f;
+                ev_p[h] = v;
+                if (WITH_BR) evbr_p[h] = v;
+            }
+        } else {  // showdown on a complete board
+            // 1. scatter the row into strength order (pos is a permutation of the live hands: deterministic)
+            for (int i = threadIdx.x; i <= R; i += blockDim.x) srt[i] = 0.0f;
+            __syncthreads();
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const int ps = pos_tab[h];
+                if (ps >= 0) srt[ps] = ro[h];
+            }
+            __syncthreads();
+            // 2. exclusive prefix sums over srt[0..R] (each thread owns a contiguous segment, then a block scan)
+            const int per = (R + 1 + blockDim.x - 1) / blockDim.x;
+            const int i0 = threadIdx.x * per, i1 = min(R + 1, i0 + per);
+            float loc = 0.0f;
+            for (int i = i0; i < i1; ++i) loc += srt[i];
+            float inc = loc;  // inclusive scan of the per-thread sums
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) wsum[wid] = inc;
+            __syncthreads();
+            if (wid == 0) {
+                float w = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0.0f;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float t = __shfl_up_sync(0xffffffffu, w, o);
+                    if (lane >= o) w += t;
+                }
+                if (lane < (blockDim.x >> 5)) wsum[lane] = w;
+            }
+            __syncthreads();
+            float run = inc - loc + (wid > 0 ? wsum[wid - 1] : 0.0f);  // exclusive prefix of this thread's segment
+            for (int i = i0; i < i1; ++i) {
+                const float x = srt[i];
+                srt[i] = run;
+                run += x;
+            }
+            __syncthreads();
+            // 3. per hand: weaker mass - stronger mass, minus the same quantity over the hands sharing a card with it
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const int gs = gs_tab[h];
+                float v = 0.0f;
+                if (gs >= 0) {
+                    const int ge = ge_tab[h];
+                    const float below = srt[gs], above = srt[R] - srt[ge];  // srt[R] = total live mass
+                    const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
+                    float corr = 0.0f;
+                    for (int x = 0; x < n_deck; ++x) {
+                        if (x == c1 || x == c2) continue;
+                        const int ha = pair_index(c1, x, n_deck), hb = pair_index(c2, x, n_deck);
+                        const int ga = gs_tab[ha], gb = gs_tab[hb];
+                        if (ga >= 0) corr += (gs > ga) ? ro[ha] : ((gs < ga) ? -ro[ha] : 0.0f);
+                        if (gb >= 0) corr += (gs > gb) ? ro[hb] : ((gs < gb) ? -ro[hb] : 0.0f);
+                    }
+                    v = (below - above - corr) * K * half_pot * 0.5f;
+                }
+                ev_p[h] = v;
+                if (WITH_BR) evbr_p[h] = v;
+            }
+        }
+    }
+}
+
+// ---- strength-order tables of complete boards: gs = # live hands strictly weaker, ge = # live hands weaker or equal,
+//      pos = unique position in strength order (ties by hand index); -1 for hands blocked by the board
+__global__ void __launch_bounds__(256) board_order_kernel(const int32_t* __restrict__ ranks, int n_boards, int R,
+                                                          int16_t* gs, int16_t* ge, int16_t* pos) {
+    extern __shared__ int srk[];
+    const int b = blockIdx.x;
+    for (int h = threadIdx.x; h < R; h += blockDim.x) srk[h] = ranks[(size_t)b * R + h];
+    __syncthreads();
+    for (int h = threadIdx.x; h < R; h += blockDim.x) {
+        const int r = srk[h];
+        int lt = 0, le = 0, tie_before = 0;
+        if (r >= 0) {
+            for (int j = 0; j < R; ++j) {
+                const int q = srk[j];
+                if (q < 0) continue;
+                lt += q < r;
+                le += q <= r;
+                tie_before += (q == r) && (j < h);
+            }
+        }
+        gs[(size_t)b * R + h] = (int16_t)(r >= 0 ? lt : -1);
+        ge[(size_t)b * R + h] = (int16_t)(r >= 0 ? le : -1);
+        pos[(size_t)b * R + h] = (int16_t)(r >= 0 ? lt + tie_before : -1);
+    }
+}
+
+// root exploitability: sum_h reach[p][0][h] * (ev_br - ev)[p][0][h]  (ValueFiller.py:95-101), double accumulation
+__global__ void root_exploitability2_kernel(prl_tree_t T, prl_buffers_t B, float* out) {
+    __shared__ double red[256];
+    const size_t N = (size_t)T.n_nodes;
+    for (int p = 0; p < 2; ++p) {
+        const float* ev = B.ev + (size_t)p * N * T.ld;
+        const float* evbr = B.ev_br + (size_t)p * N * T.ld;
+        const float* reach = B.reach + (size_t)p * N * T.ld;
+        double s = 0.0;
+        for (int h = threadIdx.x; h < T.n_range; h += blockDim.x) s += (double)reach[h] * ((double)evbr[h] - (double)ev[h]);
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[p] = (float)red[0];
+        __syncthreads();
+    }
+}
+
+inline unsigned blocks_for(long long threads) { return (unsigned)((threads + kThreads - 1) / kThreads); }
+
+int check_tree2(const prl_tree_t* t) {
+    if (!t || !t->level_start || !t->order || !t->level_nonterm || !t->level_ndec)
+        return prl::fail("prl(two-card): level_start / order / level_nonterm / level_ndec missing");
+    if (!t->hand_cards || !t->board_mask || !t->board_prob || !t->board_mult)
+        return prl::fail("prl(two-card): hand_cards / board tables missing");
+    if (t->n_sym > 1 && !t->sym_perm) return prl::fail("prl(two-card): sym_perm missing");
+    return 0;
+}
+
+size_t term_smem(const prl_tree_t& T) { return sizeof(float) * ((size_t)2 * T.n_range + 1 + 64 + 32 + kTermThreads / 32 + 1); }
+
+void reach_sweep2(Ctx2 c, bool update_avg, cudaStream_t s) {
+    const prl_tree_t& T = c.T;
+    for (int d = 0; d < T.n_levels; ++d) {
+        c.lo = (int)T.level_start[d];
+        c.n = (int)(T.level_start[d + 1] - T.level_start[d]);
+        if (c.n == 0) continue;
+        const unsigned g = blocks_for((long long)c.n * T.ld);
+        if (update_avg) reach2_kernel<true><<<g, kThreads, 0, s>>>(c);
+        else reach2_kernel<false><<<g, kThreads, 0, s>>>(c);
+        prl::count_launch();
+    }
+}
+
+int value_sweep2(Ctx2 c, bool with_br, bool update, cudaStream_t s) {
+    const prl_tree_t& T = c.T;
+    static bool smem_set = false;
+    const size_t tsm = term_smem(T);
+    if (!smem_set) {
+        cudaFuncSetAttribute(terminal2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        smem_set = true;
+    }
+    int arr_mask = 0;
+    for (int p = 0; p < 2; ++p)
+        if (c.mask & (1 << p)) arr_mask |= (1 << (2 * p)) | (with_br ? (2 << (2 * p)) : 0);
+    for (int d = T.n_levels - 1; d >= 0; --d) {
+        const int lo = (int)T.level_start[d], n_all = (int)(T.level_start[d + 1] - T.level_start[d]);
+        const int n_dec = (int)T.level_ndec[d], n_nonterm = (int)T.level_nonterm[d];
+        const int n_chance = n_nonterm - n_dec, n_term = n_all - n_nonterm;
+        if (n_term > 0) {
+            c.lo = lo + n_nonterm;
+            c.n = n_term;
+            if (with_br) terminal2_kernel<true><<<n_term, kTermThreads, tsm, s>>>(c);
+            else terminal2_kernel<false><<<n_term, kTermThreads, tsm, s>>>(c);
+            prl::count_launch();
+        }
+        if (n_dec > 0) {
+            c.lo = lo;
+            c.n = n_dec;
+            const unsigned g = blocks_for((long long)n_dec * T.ld);
+            if (update) value2_kernel<false, true><<<g, kThreads, 0, s>>>(c);
+            else if (with_br) value2_kernel<true, false><<<g, kThreads, 0, s>>>(c);
+            else value2_kernel<false, false><<<g, kThreads, 0, s>>>(c);
+            prl::count_launch();
+        }
+        if (n_chance > 0) {
+            c.lo = lo + n_dec;
+            c.n = n_chance;
+            ChanceGeom g;
+            g.n_chance = n_chance;
+            g.max_chunks = (T.max_chance_children + kChanceChunk - 1) / kChanceChunk;
+            g.w_off = (size_t)4 * n_chance * g.max_chunks * T.ld;
+            const size_t need = (g.w_off + (size_t)4 * n_chance * T.ld) * sizeof(float);
+            if (!c.B.workspace || c.B.workspace_bytes < need) return prl::fail("prl(two-card): workspace too small for the chance reduction");
+            chance_partial_kernel<<<n_chance * g.max_chunks, kThreads, 0, s>>>(c, g, arr_mask);
+            chance_sum_kernel<<<blocks_for((long long)n_chance * T.ld), kThreads, 0, s>>>(c, g, arr_mask);
+            chance_final_kernel<<<blocks_for((long long)n_chance * T.ld), kThreads, 0, s>>>(c, g, arr_mask);
+            prl::count_launch();
+            prl::count_launch();
+            prl::count_launch();
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+// entry points used by the dispatchers in cfr_levels.cu when tree->n_hole == 2
+namespace prl2 {
+
+int reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, const int* mode, cudaStream_t s) {
+    if (int e = check_tree2(tree)) return e;
+    Ctx2 c{*tree, *buf, 0, 0, player_mask, {mode[0], mode[1]}, 0, -1, 0, 0};
+    reach_sweep2(c, false, s);
+    return prl::check(cudaGetLastError(), "prl_reach_pass(two-card)");
+}
+
+int value_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int with_br, const int* mode,
+               cudaStream_t s) {
+    if (int e = check_tree2(tree)) return e;
+    Ctx2 c{*tree, *buf, 0, 0, player_mask, {mode[0], mode[1]}, 0, -1, 0, 0};
+    if (int e = value_sweep2(c, with_br != 0, false, s)) return e;
+    return prl::check(cudaGetLastError(), "prl_value_pass(two-card)");
+}
+
+int root_exploitability(const prl_tree_t* tree, const prl_buffers_t* buf, float* out, cudaStream_t s) {
+    root_exploitability2_kernel<<<1, 256, 0, s>>>(*tree, *buf, out);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_root_exploitability(two-card)");
+}
+
+int cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay, const int* mode,
+              int which, cudaStream_t s) {
+    if (int e = check_tree2(tree)) return e;
+    Ctx2 c{*tree, *buf, 0, 0, 1 << p, {mode[0], mode[1]}, algo, p, iter, delay};
+    if (which & 1)
+        if (int e = value_sweep2(c, false, true, s)) return e;
+    if (which & 2) {
+        c.mode[p] = PRL_STRAT_F32;
+        reach_sweep2(c, true, s);
+    }
+    return prl::check(cudaGetLastError(), "prl_cfr_sweep(two-card)");
+}
+
+}  // namespace prl2
+
+extern "C" int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_range, int16_t* gs, int16_t* ge,
+                                      int16_t* pos, prl_stream_t stream) {
+    if (n_boards <= 0) return 0;
+    board_order_kernel<<<n_boards, 256, sizeof(int) * n_range, (cudaStream_t)stream>>>(ranks, n_boards, n_range, gs, ge, pos);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_board_order_tables");
+}

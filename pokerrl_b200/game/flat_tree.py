@@ -108,13 +108,32 @@ def make_board_tables(rules, n_cdepth, root_board=()):
 class FlatTree:
     """Depth-sorted structure-of-arrays public tree (host numpy; uploaded to HBM by the solver)."""
 
-    def __init__(self, game_cls, env_args, stop_at_street=None, board_tables=None):
+    def __init__(self, game_cls, env_args, stop_at_street=None, board_tables=None, board_spec=None):
+        """board_spec (two-card games): a `holdem_boards.BoardSpec` naming the boards dealt at the single chance layer,
+        their deal probability, their weight in the parent's sum and the suit-permutation tables; default = all boards
+        of the game as suit-isomorphism classes."""
         self.game_cls = game_cls
         self.rules = game_cls.RULES
         self.R = self.rules.RANGE_SIZE
         self.betting = eng.HUBetting(game_cls, env_args)
         self.abs_nodes = enumerate_betting_tree(self.betting, stop_at_street=stop_at_street)
+        self.board_spec = None
+        if self.rules.N_HOLE_CARDS == 2:
+            from pokerrl_b200.game.holdem_boards import BoardSpec
+            n_cd = max(n.cdepth for n in self.abs_nodes)
+            if n_cd > 1:
+                raise NotImplementedError("two-card games with more than one chance layer (turn/river deals)")
+            if any(n.kind == KIND_SHOWDOWN_ALLIN for n in self.abs_nodes):
+                raise NotImplementedError("all-in showdowns before the board is complete in two-card games")
+            if board_spec is None:
+                board_spec = BoardSpec.full_game(self.rules)
+            self.board_spec = board_spec
+            board_tables = ([np.zeros((1, 0), np.int8), board_spec.boards],
+                            [np.zeros(1, np.int32), np.zeros(board_spec.boards.shape[0], np.int32)])
         self._expand(board_tables)
+        if self.board_spec is not None:  # per global board id (0 = the empty pre-deal board)
+            self.board_prob = np.concatenate([[1.0], self.board_spec.board_prob]).astype(np.float32)
+            self.board_mult = np.concatenate([[1.0], self.board_spec.board_mult]).astype(np.float32)
 
     # ------------------------------------------------------------------
     def _expand(self, board_tables):

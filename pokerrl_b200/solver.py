@@ -33,8 +33,9 @@ class DeviceTree:
         self.device = _require_cuda(device)
         rules = ft.rules
         self.R = ft.R
-        # row stride = R (measured on B200: padding Leduc rows 6 -> 8 floats to whole 32-byte sectors was 8 % slower)
-        self.ld = ft.R
+        # row stride: R for the one-card games (measured on B200: padding Leduc rows 6 -> 8 floats was 8 % slower);
+        # two-card rows (R = 1326) are padded to a multiple of 4 floats so that every row starts 16-byte aligned
+        self.ld = ft.R if rules.N_HOLE_CARDS == 1 else -(-ft.R // 4) * 4
         dev = self.device
 
         def up(a, dt):
@@ -78,9 +79,66 @@ class DeviceTree:
             fc0 = ft.first_child[ch[0]] if ch.size else 0
             assert ch.size == 0 or np.array_equal(board[fc0:fc0 + rules.N_CARDS_IN_DECK],
                                                   np.arange(rules.N_CARDS_IN_DECK))
-        self.t_meta = torch.zeros(ft.n_nodes, 4, dtype=torch.int32, device=dev)
-        nat.call("prl_pack_node_meta", C.byref(d), C.c_void_p(self.t_meta.data_ptr()), _stream())
-        d.meta = self.t_meta.data_ptr()
+        if rules.N_HOLE_CARDS == 1:
+            self.t_meta = torch.zeros(ft.n_nodes, 4, dtype=torch.int32, device=dev)
+            nat.call("prl_pack_node_meta", C.byref(d), C.c_void_p(self.t_meta.data_ptr()), _stream())
+            d.meta = self.t_meta.data_ptr()
+        else:
+            self._init_two_card(ft, d, up)
+
+    def _init_two_card(self, ft, d, up):
+        """Board tables of the Hold'em family: card masks, deal probabilities, parent weights, strength-order tables
+        (hand ranks by the GPU evaluator, then prl_board_order_tables), suit-permutation tables."""
+        from math import comb
+        from pokerrl_b200.hand_eval import hand_rank_all_hands_on_given_boards
+        rules, dev = ft.rules, self.device
+        lut = rules.get_lut_holder()
+        self.t_hand_cards = up(lut.LUT_IDX_2_HOLE_CARDS, np.int8)
+        bc = ft.board_cards()  # [n_boards_total, n_board_cards], global board id order
+        nb = bc.shape[0]
+        mask = np.zeros(nb, np.uint64)
+        for k in range(bc.shape[1]):
+            live = bc[:, k] >= 0
+            mask[live] |= (np.uint64(1) << bc[live, k].astype(np.uint64))
+        self.t_board_mask = torch.from_numpy(mask.view(np.int64)).to(dev)
+        self.t_board_prob = up(ft.board_prob, np.float32)
+        self.t_board_mult = up(ft.board_mult, np.float32)
+        complete = np.nonzero((bc >= 0).sum(axis=1) == 5)[0]
+        gs = torch.full((nb, self.R), -1, dtype=torch.int16, device=dev)
+        ge, pos = torch.full_like(gs, -1), torch.full_like(gs, -1)
+        self.t_board_ranks = torch.full((nb, self.R), -1, dtype=torch.int32, device=dev)
+        CH = 16384
+        for i in range(0, complete.size, CH):
+            ids = torch.from_numpy(complete[i:i + CH]).to(dev)
+            ranks = hand_rank_all_hands_on_given_boards(bc[complete[i:i + CH]], device=dev)
+            self.t_board_ranks[ids] = ranks
+            g1, g2, g3 = (torch.empty((ids.numel(), self.R), dtype=torch.int16, device=dev) for _ in range(3))
+            nat.call("prl_board_order_tables", C.c_void_p(ranks.data_ptr()), int(ids.numel()), self.R,
+                     C.c_void_p(g1.data_ptr()), C.c_void_p(g2.data_ptr()), C.c_void_p(g3.data_ptr()), _stream())
+            gs[ids], ge[ids], pos[ids] = g1, g2, g3
+        self.t_board_gs, self.t_board_ge, self.t_board_pos = gs, ge, pos
+        sp = ft.board_spec.sym_perm
+        self.t_sym_perm = up(sp, np.int16) if sp is not None else None
+        dec_per_level = [int(((ft.kind[int(ft.level_start[k]):int(ft.level_start[k + 1])] <= nat.KIND_P1)).sum())
+                         for k in range(ft.n_levels)]
+        self._level_ndec = np.ascontiguousarray(dec_per_level, dtype=np.int64)
+        ch = ft.kind == nat.KIND_CHANCE
+        d.level_ndec = self._level_ndec.ctypes.data
+        d.hand_cards = self.t_hand_cards.data_ptr()
+        d.n_boards = nb
+        d.max_chance_children = int(ft.n_children[ch].max()) if ch.any() else 0
+        d.board_mask, d.board_prob = self.t_board_mask.data_ptr(), self.t_board_prob.data_ptr()
+        d.board_mult = self.t_board_mult.data_ptr()
+        d.board_gs, d.board_ge, d.board_pos = gs.data_ptr(), ge.data_ptr(), pos.data_ptr()
+        d.n_sym = 0 if sp is None else int(sp.shape[0])
+        d.sym_perm = self.t_sym_perm.data_ptr() if sp is not None else None
+        n_deck, n_hole = rules.N_CARDS_IN_DECK, rules.N_HOLE_CARDS
+        d.eq_const = comb(n_deck, n_hole) / comb(n_deck - n_hole, n_hole)
+        # scratch of the chance-node reductions (see prl_buffers_t.workspace)
+        max_chance_per_level = max([int((ft.kind[int(ft.level_start[k]):int(ft.level_start[k + 1])] == nat.KIND_CHANCE).sum())
+                                    for k in range(ft.n_levels)] + [0])
+        chunks = -(-d.max_chance_children // 128)
+        self.workspace_bytes = 4 * max(1, max_chance_per_level) * (chunks + 1) * self.ld * 4
 
     @property
     def n_nodes(self):
@@ -107,6 +165,10 @@ class TreeBuffers:
             self.ev, self.ev_br = share.ev, share.ev_br
             self.regret, self.strat, self.avg = share.regret, share.strat, share.avg
         d = nat.PrlBuffers()
+        wb = getattr(dtree, "workspace_bytes", 0)
+        if wb:
+            self.workspace = share.workspace if share is not None else torch.zeros(wb // 4, dtype=torch.float32, device=dev)
+            d.workspace, d.workspace_bytes = self.workspace.data_ptr(), wb
         d.reach, d.ev, d.ev_br = self.reach.data_ptr(), self.ev.data_ptr(), self.ev_br.data_ptr()
         d.regret = self.regret.data_ptr() if self.regret is not None else None
         d.strat = self.strat.data_ptr() if self.strat is not None else None

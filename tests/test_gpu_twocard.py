@@ -1,0 +1,85 @@
+"""GPU parity of the two-card (Hold'em family) sweeps against the float64 oracle (oracle/cfr2_numpy.py).
+
+Tolerance: float32 device arithmetic vs float64 oracle - node vectors within 2e-5 of the largest magnitude of the
+compared array, exploitability within 1e-5 relative (BASELINE.json's 1e-6 is stated against the reference's own
+float32 path, which does not exist for these games)."""
+import numpy as np
+import pytest
+
+import cfr2_numpy as o2
+from pokerrl_b200.game.holdem_boards import BoardSpec
+from pokerrl_b200.game.games import FlopHoldemRules
+from twocard_common import fhp_tree, oracle_tree, random_board_spec
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(name, mine, ref, tol=2e-5):
+    scale = np.abs(ref).max()
+    err = np.abs(mine - ref).max()
+    assert err <= tol * scale, (name, err, scale)
+
+
+def _node_vec(s_t, ft):  # torch [2, N, ld] -> [N, 2, R]
+    return s_t.cpu().numpy()[:, :, :ft.R].transpose(1, 0, 2).astype(np.float64)
+
+
+def test_uniform_profile_values_random_boards():
+    from pokerrl_b200.solver import CFRSolver
+    ft = fhp_tree(random_board_spec(24, 1))
+    orc = oracle_tree(ft)
+    orc.fill_uniform()
+    expl = orc.compute_ev()
+    s = CFRSolver(ft, "CFRPlus")
+    m = s.exploitability_current()
+    _close("reach", _node_vec(s.bufs.reach, ft), orc.reach)
+    _close("ev", _node_vec(s.bufs.ev, ft), orc.ev)
+    _close("ev_br", _node_vec(s.bufs.ev_br, ft), orc.ev_br)
+    ref_m = float(sum(expl) / 2 * ft.game_cls.EV_NORMALIZER)
+    assert abs(m - ref_m) <= 1e-5 * abs(ref_m), (m, ref_m)
+    # zero-sum check of the reference (ValueFiller.py:98) at the root
+    assert abs((orc.ev[0] * orc.reach[0]).sum()) < 1e-6 * np.abs(orc.ev[0]).max()
+
+
+@pytest.mark.parametrize("algo", ["CFRPlus", "LinearCFR", "VanillaCFR"])
+def test_cfr_iterations_match_oracle(algo):
+    from pokerrl_b200.solver import CFRSolver
+    ft = fhp_tree(random_board_spec(16, 2))
+    s = CFRSolver(ft, algo)
+    c = o2.Oracle2CFR(oracle_tree(ft), algo, ev_normalizer=ft.game_cls.EV_NORMALIZER)
+    for t in range(4):
+        s.iteration(1)
+        c.iteration()
+        reg = s.bufs.regret.cpu().numpy()[:, :ft.R].astype(np.float64)
+        ref = np.zeros_like(reg)
+        for n in c.t.decision_nodes():
+            ref[ft.first_slot[n]:ft.first_slot[n] + ft.n_children[n]] = c.regret[n].T
+        _close("regret it%d" % t, reg, ref, tol=5e-5)
+        a, b = s.exploitability_current(), c.exploitability_current()
+        assert abs(a - b) <= 2e-5 * abs(b), (t, a, b)
+        a, b = s.exploitability_average(), c.exploitability_average()
+        assert abs(a - b) <= 2e-5 * abs(b), (t, a, b)
+
+
+def test_suit_isomorphism_equals_full_enumeration():
+    """Representatives + orbit weights + symmetrisation reproduce the evaluation over every board of a
+    suit-closed deck subset (ranks 2 and A in four suits: 56 boards)."""
+    from pokerrl_b200.solver import CFRSolver
+    deck = [0, 1, 2, 3, 48, 49, 50, 51]
+    full = fhp_tree(BoardSpec.full_game(FlopHoldemRules, isomorphic=False, deck_subset=deck))
+    iso = fhp_tree(BoardSpec.full_game(FlopHoldemRules, isomorphic=True, deck_subset=deck))
+    assert iso.board_spec.boards.shape[0] < full.board_spec.boards.shape[0] == 56
+    s_full, s_iso = CFRSolver(full, "CFRPlus"), CFRSolver(iso, "CFRPlus")
+    orc = o2.Oracle2CFR(oracle_tree(full), "CFRPlus", ev_normalizer=full.game_cls.EV_NORMALIZER)
+    for t in range(3):
+        a, b, c = s_full.exploitability_current(), s_iso.exploitability_current(), orc.exploitability_current()
+        assert abs(a - c) <= 2e-5 * abs(c) and abs(b - c) <= 2e-5 * abs(c), (t, a, b, c)
+        # trunk (pre-deal) regrets agree between the two GPU trees and with the oracle
+        ra = s_full.bufs.regret[:4, :full.R].cpu().numpy()
+        rb = s_iso.bufs.regret[:4, :iso.R].cpu().numpy()
+        _close("trunk regret", rb, ra.astype(np.float64), tol=5e-5) if t else None
+        s_full.iteration(1)
+        s_iso.iteration(1)
+        orc.iteration()
+    a, b, c = s_full.exploitability_average(), s_iso.exploitability_average(), orc.exploitability_average()
+    assert abs(a - c) <= 2e-5 * abs(c) and abs(b - c) <= 2e-5 * abs(c), (a, b, c)

@@ -1,0 +1,44 @@
+"""Helpers for the two-card (Hold'em family) parity tests."""
+import ctypes as C
+import os
+
+import numpy as np
+
+import cfr2_numpy as o2
+from pokerrl_b200.game import games
+from pokerrl_b200.game.flat_tree import FlatTree
+from pokerrl_b200.game.holdem_boards import BoardSpec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fhp_tree(board_spec, stack=20000):
+    g = games.Flop5Holdem
+    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[stack, stack], bet_sizes_list_as_frac_of_pot=[1.0])
+    return FlatTree(g, args, board_spec=board_spec)
+
+
+def oracle_ranks(boards):
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    orc = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libhand_eval_oracle.so"))
+    orc.orc_rank_boards.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    boards = np.ascontiguousarray(boards, np.int8)
+    out = np.zeros((len(boards), 1326), np.int32)
+    orc.orc_rank_boards(out.ctypes.data, boards.ctypes.data, len(boards))
+    return out
+
+
+def oracle_tree(ft):
+    """float64 oracle over the same flat tree / board spec"""
+    spec = ft.board_spec
+    lut = ft.rules.get_lut_holder()
+    ranks = np.concatenate([np.full((1, ft.R), -1, np.int32), oracle_ranks(spec.boards)])
+    return o2.Oracle2Tree(ft, lut.LUT_IDX_2_HOLE_CARDS, ranks, ft.board_prob, ft.board_mult, spec.sym_perm)
+
+
+def random_board_spec(n, seed):
+    rng = np.random.default_rng(seed)
+    boards = np.unique(np.sort(np.stack([rng.choice(52, 5, replace=False) for _ in range(n)]), axis=1), axis=0)
+    return BoardSpec(boards.astype(np.int8), np.full(len(boards), 1.0 / len(boards)), np.ones(len(boards)), None,
+                     "%d random boards" % len(boards))
