@@ -88,6 +88,10 @@ typedef struct {
     const int16_t* board_gs;     /* DEVICE int16[n_boards][n_range]: # live hands strictly weaker (-1: hand blocked)   */
     const int16_t* board_ge;     /* DEVICE int16[n_boards][n_range]: # live hands weaker or equal                      */
     const int16_t* board_pos;    /* DEVICE int16[n_boards][n_range]: position in strength order (prl_board_order_tables) */
+    const int16_t* board_row_order; /* DEVICE int16[n_boards][n_deck][n_deck-1]: per card, the live hands holding it in
+                                       strength order (-1 padded) */
+    const uint8_t* board_row_pos;   /* DEVICE uint8[n_boards][n_range][4]: per hand {# weaker in row c1, # weaker in row
+                                       c2, # weaker-or-equal in row c1, in row c2} */
     int32_t n_sym;               /* hand permutations summed at chance parents (24 suit permutations with isomorphism, else 0/1) */
     const int16_t* sym_perm;     /* DEVICE int16[n_sym][n_range] */
     float eq_const;              /* opponent-hand normaliser C(deck,2)/C(deck-2,2) (ValueFiller.py:19 generalised) */
@@ -161,10 +165,24 @@ void prl_debug_set_timeline(void* device_u64_buffer);
 int prl_cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay, int avg_f64,
                   const int* strat_mode, int which, prl_stream_t stream);
 
+/* Multi-GPU building blocks (two-card trees sharded by board).  prl_value_levels runs the bottom-up sweep
+ * over levels level_hi..level_lo only; algo >= 0 makes it the update sweep of seat upd_p (else a plain value pass, with
+ * best response if with_br).  chance_phase 1 stops before the final stage of the chance reduction, leaving the per-node
+ * sums in buf->workspace at float offset 4*n_chance*ceil(max_chance_children/128)*ld, laid out [4][n_chance][ld]
+ * (array index = 2*seat + {0: ev, 1: ev_br}) so that the caller can all-reduce them over the ranks (the ONE collective
+ * of the path); chance_phase 2 runs only that final stage; 0 runs whole levels.
+ * prl_reach_update is the top-down half of prl_cfr_half_iteration for seat p. */
+int prl_value_levels(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int with_br, int algo, int upd_p,
+                     int iter, int delay, const int* strat_mode, int level_hi, int level_lo, int chance_phase,
+                     prl_stream_t stream);
+int prl_reach_update(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
+                     prl_stream_t stream);
+
 /* Strength-order tables of complete boards for the two-card showdown rows: ranks = DEVICE int32[n_boards][n_range]
- * (prl_hand_rank_boards; -1 = blocked) -> gs / ge / pos = DEVICE int16[n_boards][n_range] (see prl_tree_t). */
-int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_range, int16_t* gs, int16_t* ge, int16_t* pos,
-                           prl_stream_t stream);
+ * (prl_hand_rank_boards; -1 = blocked) -> gs / ge / pos = DEVICE int16[n_boards][n_range], row_order = DEVICE
+ * int16[n_boards][n_deck][n_deck-1], row_pos = DEVICE uint8[n_boards][n_range][4] (see prl_tree_t). */
+int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_range, int n_deck, int16_t* gs, int16_t* ge,
+                           int16_t* pos, int16_t* row_order, uint8_t* row_pos, prl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * 7-card Hold'em hand evaluation (replaces lib_hand_eval.so; int32 strength, higher = better, identical encoding incl.

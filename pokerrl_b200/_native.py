@@ -27,6 +27,7 @@ class PrlTree(C.Structure):
         ("level_ndec", C.c_void_p), ("hand_cards", C.c_void_p), ("n_boards", C.c_int32),
         ("max_chance_children", C.c_int32), ("board_mask", C.c_void_p), ("board_prob", C.c_void_p),
         ("board_mult", C.c_void_p), ("board_gs", C.c_void_p), ("board_ge", C.c_void_p), ("board_pos", C.c_void_p),
+        ("board_row_order", C.c_void_p), ("board_row_pos", C.c_void_p),
         ("n_sym", C.c_int32), ("sym_perm", C.c_void_p), ("eq_const", C.c_float),
     ]
 
@@ -65,7 +66,12 @@ def lib():
     for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration", "prl_cfr_sweep", "prl_pack_node_meta", "prl_cfr_iterations",
               "prl_evaluate"):
         getattr(L, f).restype = C.c_int
-    L.prl_board_order_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.prl_value_levels.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p]
+    L.prl_reach_update.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.prl_value_levels.restype = L.prl_reach_update.restype = C.c_int
+    L.prl_board_order_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
     L.prl_board_order_tables.restype = C.c_int
     L.prl_hand_rank_boards.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.prl_hand_rank_7.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -23,6 +23,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kTermThreads = 512;
+constexpr int kRowStride = 53;     // n_deck - 1 hands per card row + 1, +1 padding against bank conflicts
 constexpr int kChanceChunk = 128;  // children summed per block in the first stage of a chance-node reduction
 
 struct Ctx2 {
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
     float* cs = srt + R + 1;               // [64]     per-card sums
     float* red = cs + 64;                  // [32]
     float* wsum = red + 32;                // [kTermThreads / 32 + 1]
+    float* rp = wsum + kTermThreads / 32 + 1;  // [n_deck][kRowStride] exclusive prefix sums of every card row (sorted)
     const int n = c.T.order[c.lo + blockIdx.x];
     const int kind = c.T.kind[n];
     const int b = c.T.board[n];
@@ -275,6 +277,8 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
     const int16_t* gs_tab = (b >= 0 && c.T.board_gs) ? c.T.board_gs + (size_t)b * R : nullptr;
     const int16_t* ge_tab = (b >= 0 && c.T.board_ge) ? c.T.board_ge + (size_t)b * R : nullptr;
     const int16_t* pos_tab = (b >= 0 && c.T.board_pos) ? c.T.board_pos + (size_t)b * R : nullptr;
+    const int16_t* row_order = (b >= 0) ? c.T.board_row_order + (size_t)b * n_deck * (n_deck - 1) : nullptr;
+    const uchar4* row_pos = (b >= 0) ? reinterpret_cast<const uchar4*>(c.T.board_row_pos) + (size_t)b * R : nullptr;
 #pragma unroll 1
     for (int p = 0; p < 2; ++p) {
         if (!(c.mask & (1 << p))) continue;
@@ -289,20 +293,38 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
         const float T = block_sum(part, red);  // includes the barrier that publishes ro[]
         float* ev_p = c.B.ev + ((size_t)p * N + n) * ld;
         float* evbr_p = WITH_BR ? c.B.ev_br + ((size_t)p * N + n) * ld : nullptr;
-        if (kind == PRL_KIND_FOLD) {
-            // per-card sums cs[x] = sum of ro over the hands containing card x (each of the first n_deck threads: one card)
-            if (threadIdx.x < n_deck) {
-                const int x = threadIdx.x;
-                float s = 0.0f;
-                for (int y = 0; y < n_deck; ++y)
-                    if (y != x) s += ro[pair_index(x, y, n_deck)];
-                cs[x] = s;
+        // exclusive prefix sums of the opponent row along every card row (the n_deck - 1 hands containing one card),
+        // taken in the board's strength order: rp[c][i] = mass of the i weakest live hands containing card c
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+        const int row_len = n_deck - 1;
+        for (int cc = warp; cc < n_deck; cc += n_warps) {
+            float v0 = 0.0f, v1 = 0.0f;
+            if (row_order) {
+                const int h0 = (lane < row_len) ? row_order[cc * row_len + lane] : -1;
+                const int h1 = (lane + 32 < row_len) ? row_order[cc * row_len + lane + 32] : -1;
+                v0 = (h0 >= 0) ? ro[h0] : 0.0f;
+                v1 = (h1 >= 0) ? ro[h1] : 0.0f;
+            } else {  // no board: any fixed order of the row (pre-deal fold terminals only need the row totals)
+                const int x0 = lane + (lane >= cc), x1 = lane + 32 + (lane + 32 >= cc);
+                v0 = (lane < row_len) ? ro[pair_index(cc, x0, n_deck)] : 0.0f;
+                v1 = (lane + 32 < row_len) ? ro[pair_index(cc, x1, n_deck)] : 0.0f;
             }
-            __syncthreads();
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t0 = __shfl_up_sync(0xffffffffu, v0, o), t1 = __shfl_up_sync(0xffffffffu, v1, o);
+                if (lane >= o) { v0 += t0; v1 += t1; }
+            }
+            v1 += __shfl_sync(0xffffffffu, v0, 31);
+            float* row = rp + cc * kRowStride;
+            if (lane == 0) row[0] = 0.0f;
+            if (lane < row_len) row[lane + 1] = v0;
+            if (lane + 32 < row_len) row[lane + 33] = v1;
+        }
+        __syncthreads();
+        if (kind == PRL_KIND_FOLD) {
             const float sgn = (c.T.acted_last[n] == p) ? -1.0f : 1.0f;
             for (int h = threadIdx.x; h < R; h += blockDim.x) {
                 const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
-                float e = (T - cs[c1] - cs[c2] + ro[h]) * sgn * K;
+                float e = (T - rp[c1 * kRowStride + row_len] - rp[c2 * kRowStride + row_len] + ro[h]) * sgn * K;
                 if (((bmask >> c1) | (bmask >> c2)) & 1ull) e = 0.0f;
                 const float v = e * half_pot * 0.5f;
                 ev_p[h] = v;
@@ -323,46 +345,42 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
             float loc = 0.0f;
             for (int i = i0; i < i1; ++i) loc += srt[i];
             float inc = loc;  // inclusive scan of the per-thread sums
-            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
             for (int o = 1; o < 32; o <<= 1) {
                 const float t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            if (lane == 31) wsum[wid] = inc;
+            if (lane == 31) wsum[warp] = inc;
             __syncthreads();
-            if (wid == 0) {
-                float w = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0.0f;
+            if (warp == 0) {
+                float w = (lane < n_warps) ? wsum[lane] : 0.0f;
                 for (int o = 1; o < 32; o <<= 1) {
                     const float t = __shfl_up_sync(0xffffffffu, w, o);
                     if (lane >= o) w += t;
                 }
-                if (lane < (blockDim.x >> 5)) wsum[lane] = w;
+                if (lane < n_warps) wsum[lane] = w;
             }
             __syncthreads();
-            float run = inc - loc + (wid > 0 ? wsum[wid - 1] : 0.0f);  // exclusive prefix of this thread's segment
+            float run = inc - loc + (warp > 0 ? wsum[warp - 1] : 0.0f);  // exclusive prefix of this thread's segment
             for (int i = i0; i < i1; ++i) {
                 const float x = srt[i];
                 srt[i] = run;
                 run += x;
             }
             __syncthreads();
-            // 3. per hand: weaker mass - stronger mass, minus the same quantity over the hands sharing a card with it
+            // 3. per hand: (weaker - stronger) mass over all live hands minus the same over the two card rows of the hand
+            //    (the hands that share a card with it; the hand itself ties with itself and drops out)
             for (int h = threadIdx.x; h < R; h += blockDim.x) {
                 const int gs = gs_tab[h];
                 float v = 0.0f;
                 if (gs >= 0) {
                     const int ge = ge_tab[h];
-                    const float below = srt[gs], above = srt[R] - srt[ge];  // srt[R] = total live mass
                     const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
-                    float corr = 0.0f;
-                    for (int x = 0; x < n_deck; ++x) {
-                        if (x == c1 || x == c2) continue;
-                        const int ha = pair_index(c1, x, n_deck), hb = pair_index(c2, x, n_deck);
-                        const int ga = gs_tab[ha], gb = gs_tab[hb];
-                        if (ga >= 0) corr += (gs > ga) ? ro[ha] : ((gs < ga) ? -ro[ha] : 0.0f);
-                        if (gb >= 0) corr += (gs > gb) ? ro[hb] : ((gs < gb) ? -ro[hb] : 0.0f);
-                    }
-                    v = (below - above - corr) * K * half_pot * 0.5f;
+                    const uchar4 q = row_pos[h];  // {weaker in row c1, weaker in row c2, weaker-or-equal c1, c2}
+                    const float* r1 = rp + c1 * kRowStride;
+                    const float* r2 = rp + c2 * kRowStride;
+                    const float all = srt[gs] - (srt[R] - srt[ge]);
+                    const float rows = (r1[q.x] - (r1[row_len] - r1[q.z])) + (r2[q.y] - (r2[row_len] - r2[q.w]));
+                    v = (all - rows) * K * half_pot * 0.5f;
                 }
                 ev_p[h] = v;
                 if (WITH_BR) evbr_p[h] = v;
@@ -397,6 +415,38 @@ __global__ void __launch_bounds__(256) board_order_kernel(const int32_t* __restr
     }
 }
 
+// ---- card-row tables of complete boards: for every card c the live hands containing c in strength order
+//      (row_order[b][c][i], -1 padded) and, per hand, how many hands of its two card rows are strictly weaker /
+//      weaker-or-equal (row_pos[b][h] = {lt(c1), lt(c2), le(c1), le(c2)})
+__global__ void __launch_bounds__(256) board_rows_kernel(const int16_t* __restrict__ gs, int n_boards, int R, int n_deck,
+                                                         int16_t* row_order, uint8_t* row_pos) {
+    extern __shared__ short sgs[];
+    const int b = blockIdx.x;
+    const int row_len = n_deck - 1;
+    for (int h = threadIdx.x; h < R; h += blockDim.x) sgs[h] = gs[(size_t)b * R + h];
+    for (int i = threadIdx.x; i < n_deck * row_len; i += blockDim.x) row_order[(size_t)b * n_deck * row_len + i] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_deck * row_len; i += blockDim.x) {
+        const int cc = i / row_len, j = i % row_len;
+        const int x = j + (j >= cc);
+        const int h = pair_index(cc, x, n_deck);
+        const int g = sgs[h];
+        if (g < 0) continue;
+        int lt = 0, le = 0, tie_before = 0;
+        for (int j2 = 0; j2 < row_len; ++j2) {
+            const int g2 = sgs[pair_index(cc, j2 + (j2 >= cc), n_deck)];
+            if (g2 < 0) continue;
+            lt += g2 < g;
+            le += g2 <= g;
+            tie_before += (g2 == g) && (j2 < j);
+        }
+        row_order[(size_t)b * n_deck * row_len + cc * row_len + lt + tie_before] = (int16_t)h;
+        const int k = (cc == min(cc, x)) ? 0 : 1;  // is cc the first (smaller) or second card of the hand?
+        row_pos[((size_t)b * R + h) * 4 + k] = (uint8_t)lt;
+        row_pos[((size_t)b * R + h) * 4 + 2 + k] = (uint8_t)le;
+    }
+}
+
 // root exploitability: sum_h reach[p][0][h] * (ev_br - ev)[p][0][h]  (ValueFiller.py:95-101), double accumulation
 __global__ void root_exploitability2_kernel(prl_tree_t T, prl_buffers_t B, float* out) {
     __shared__ double red[256];
@@ -423,13 +473,16 @@ inline unsigned blocks_for(long long threads) { return (unsigned)((threads + kTh
 int check_tree2(const prl_tree_t* t) {
     if (!t || !t->level_start || !t->order || !t->level_nonterm || !t->level_ndec)
         return prl::fail("prl(two-card): level_start / order / level_nonterm / level_ndec missing");
-    if (!t->hand_cards || !t->board_mask || !t->board_prob || !t->board_mult)
+    if (!t->hand_cards || !t->board_mask || !t->board_prob || !t->board_mult || !t->board_row_order || !t->board_row_pos)
         return prl::fail("prl(two-card): hand_cards / board tables missing");
+    if (t->n_deck - 1 > 64 || t->n_deck - 1 >= kRowStride) return prl::fail("prl(two-card): deck too large for the card-row scans");
     if (t->n_sym > 1 && !t->sym_perm) return prl::fail("prl(two-card): sym_perm missing");
     return 0;
 }
 
-size_t term_smem(const prl_tree_t& T) { return sizeof(float) * ((size_t)2 * T.n_range + 1 + 64 + 32 + kTermThreads / 32 + 1); }
+size_t term_smem(const prl_tree_t& T) {
+    return sizeof(float) * ((size_t)2 * T.n_range + 1 + 64 + 32 + kTermThreads / 32 + 1 + (size_t)T.n_deck * kRowStride);
+}
 
 void reach_sweep2(Ctx2 c, bool update_avg, cudaStream_t s) {
     const prl_tree_t& T = c.T;
@@ -444,7 +497,9 @@ void reach_sweep2(Ctx2 c, bool update_avg, cudaStream_t s) {
     }
 }
 
-int value_sweep2(Ctx2 c, bool with_br, bool update, cudaStream_t s) {
+// levels d_hi .. d_lo (bottom-up).  chance_phase: 0 = whole levels; 1 = everything except the final stage of the chance
+// reduction (the per-node sums W stay in the workspace, e.g. to be all-reduced across GPUs); 2 = only that final stage
+int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int chance_phase, cudaStream_t s) {
     const prl_tree_t& T = c.T;
     static bool smem_set = false;
     const size_t tsm = term_smem(T);
@@ -456,18 +511,18 @@ int value_sweep2(Ctx2 c, bool with_br, bool update, cudaStream_t s) {
     int arr_mask = 0;
     for (int p = 0; p < 2; ++p)
         if (c.mask & (1 << p)) arr_mask |= (1 << (2 * p)) | (with_br ? (2 << (2 * p)) : 0);
-    for (int d = T.n_levels - 1; d >= 0; --d) {
+    for (int d = d_hi; d >= d_lo; --d) {
         const int lo = (int)T.level_start[d], n_all = (int)(T.level_start[d + 1] - T.level_start[d]);
         const int n_dec = (int)T.level_ndec[d], n_nonterm = (int)T.level_nonterm[d];
         const int n_chance = n_nonterm - n_dec, n_term = n_all - n_nonterm;
-        if (n_term > 0) {
+        if (n_term > 0 && chance_phase != 2) {
             c.lo = lo + n_nonterm;
             c.n = n_term;
             if (with_br) terminal2_kernel<true><<<n_term, kTermThreads, tsm, s>>>(c);
             else terminal2_kernel<false><<<n_term, kTermThreads, tsm, s>>>(c);
             prl::count_launch();
         }
-        if (n_dec > 0) {
+        if (n_dec > 0 && chance_phase != 2) {
             c.lo = lo;
             c.n = n_dec;
             const unsigned g = blocks_for((long long)n_dec * T.ld);
@@ -485,15 +540,23 @@ int value_sweep2(Ctx2 c, bool with_br, bool update, cudaStream_t s) {
             g.w_off = (size_t)4 * n_chance * g.max_chunks * T.ld;
             const size_t need = (g.w_off + (size_t)4 * n_chance * T.ld) * sizeof(float);
             if (!c.B.workspace || c.B.workspace_bytes < need) return prl::fail("prl(two-card): workspace too small for the chance reduction");
-            chance_partial_kernel<<<n_chance * g.max_chunks, kThreads, 0, s>>>(c, g, arr_mask);
-            chance_sum_kernel<<<blocks_for((long long)n_chance * T.ld), kThreads, 0, s>>>(c, g, arr_mask);
-            chance_final_kernel<<<blocks_for((long long)n_chance * T.ld), kThreads, 0, s>>>(c, g, arr_mask);
-            prl::count_launch();
-            prl::count_launch();
-            prl::count_launch();
+            if (chance_phase != 2) {
+                chance_partial_kernel<<<n_chance * g.max_chunks, kThreads, 0, s>>>(c, g, arr_mask);
+                chance_sum_kernel<<<blocks_for((long long)n_chance * T.ld), kThreads, 0, s>>>(c, g, arr_mask);
+                prl::count_launch();
+                prl::count_launch();
+            }
+            if (chance_phase != 1) {
+                chance_final_kernel<<<blocks_for((long long)n_chance * T.ld), kThreads, 0, s>>>(c, g, arr_mask);
+                prl::count_launch();
+            }
         }
     }
     return 0;
+}
+
+int value_sweep2(Ctx2 c, bool with_br, bool update, cudaStream_t s) {
+    return value_levels2(c, with_br, update, c.T.n_levels - 1, 0, 0, s);
 }
 
 }  // namespace
@@ -537,10 +600,36 @@ int cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p,
 
 }  // namespace prl2
 
-extern "C" int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_range, int16_t* gs, int16_t* ge,
-                                      int16_t* pos, prl_stream_t stream) {
+// Bottom-up value sweep over tree levels level_hi .. level_lo only (two-card trees), with the chance reduction optionally
+// split around an external all-reduce of the per-chance-node sums (see include/pokerrl_b200.h).
+extern "C" int prl_value_levels(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int with_br, int algo,
+                                int upd_p, int iter, int delay, const int* strat_mode, int level_hi, int level_lo,
+                                int chance_phase, prl_stream_t stream) {
+    if (!tree || tree->n_hole != 2) return prl::fail("prl_value_levels: two-card trees only");
+    if (int e = check_tree2(tree)) return e;
+    if (level_hi >= tree->n_levels || level_lo < 0 || level_hi < level_lo) return prl::fail("prl_value_levels: bad level range");
+    if (with_br && algo >= 0) return prl::fail("prl_value_levels: the update sweep does not compute best responses");
+    Ctx2 c{*tree, *buf, 0, 0, player_mask, {strat_mode[0], strat_mode[1]}, algo < 0 ? 0 : algo, algo < 0 ? -1 : upd_p, iter, delay};
+    if (int e = value_levels2(c, with_br != 0, algo >= 0, level_hi, level_lo, chance_phase, (cudaStream_t)stream)) return e;
+    return prl::check(cudaGetLastError(), "prl_value_levels");
+}
+
+// Top-down reach sweep of seat p with the average-strategy update of p's nodes (second half of prl_cfr_half_iteration).
+extern "C" int prl_reach_update(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
+                                prl_stream_t stream) {
+    if (!tree || tree->n_hole != 2) return prl::fail("prl_reach_update: two-card trees only");
+    const int mode[2] = {PRL_STRAT_F32, PRL_STRAT_F32};
+    return prl2::cfr_sweep(tree, buf, algo, p, iter, delay, mode, 2, (cudaStream_t)stream);
+}
+
+extern "C" int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_range, int n_deck, int16_t* gs,
+                                      int16_t* ge, int16_t* pos, int16_t* row_order, uint8_t* row_pos,
+                                      prl_stream_t stream) {
     if (n_boards <= 0) return 0;
     board_order_kernel<<<n_boards, 256, sizeof(int) * n_range, (cudaStream_t)stream>>>(ranks, n_boards, n_range, gs, ge, pos);
+    board_rows_kernel<<<n_boards, 256, sizeof(short) * n_range, (cudaStream_t)stream>>>(gs, n_boards, n_range, n_deck,
+                                                                                      row_order, row_pos);
+    prl::count_launch();
     prl::count_launch();
     return prl::check(cudaGetLastError(), "prl_board_order_tables");
 }

@@ -1,0 +1,93 @@
+"""Multi-GPU CFR for two-card games: public-chance subtrees (boards) sharded over the ranks of one node.
+
+SURVEY.md §8(e): below a chance node the board subtrees are independent given the parent's reach rows
+(`StrategyFiller.py:137-140`) and contribute additively to the parent's values (`ValueFiller.py:76-78`).  Every rank
+(one process per GPU, `torch.distributed` / NCCL over NVLink) owns the regret / average tables and node vectors of ITS
+boards and a replica of the tiny pre-deal trunk.  Top-down sweeps need no communication; in a bottom-up sweep each rank
+reduces its boards into the per-chance-node sums W (board_mult-weighted) and ONE all-reduce(sum) of W - [4][n_chance][ld]
+floats, 21 KB per chance node and seat - makes the trunk values identical on all ranks, which then update the trunk
+regrets redundantly.  Nothing else crosses GPUs.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from pokerrl_b200 import _native as nat
+from pokerrl_b200.game.flat_tree import FlatTree
+from pokerrl_b200.game.holdem_boards import BoardSpec
+from pokerrl_b200.solver import CFRSolver, TreeBuffers, TreeOps, _stream
+
+
+def shard_board_spec(spec, rank, world):
+    """boards rank, rank + world, ... of `spec` (every board subtree has the same cost, so round-robin balances)"""
+    sel = np.arange(rank, spec.boards.shape[0], world)
+    return BoardSpec(spec.boards[sel], spec.board_prob[sel], spec.board_mult[sel], spec.sym_perm,
+                     "%s; shard %d/%d (%d boards)" % (spec.note, rank, world, sel.size))
+
+
+class ShardedCFRSolver(CFRSolver):
+    """CFRSolver whose bottom-up sweeps are split around an all-reduce of the chance-node sums.
+    world == 1 (or no process group) runs the same split schedule without communication."""
+
+    def __init__(self, game_cls, env_args, board_spec, algo="CFRPlus", delay=0, device=None, rank=0, world=1,
+                 group=None):
+        self.rank, self.world, self.group = rank, world, group
+        ft = FlatTree(game_cls, env_args, board_spec=shard_board_spec(board_spec, rank, world) if world > 1 else board_spec)
+        self.ft = ft
+        super().__init__(ft, algo=algo, delay=delay, device=device, avg_f64=False, persistent=False)
+        self._chance_levels = [d for d in range(ft.n_levels)
+                               if np.any(ft.kind[int(ft.level_start[d]):int(ft.level_start[d + 1])] == nat.KIND_CHANCE)]
+        self.n_allreduce = 0
+
+    # ---- the one collective of the path
+    def _allreduce_chance_sums(self, bufs, level):
+        ft, dt = self.ft, self.dtree
+        n_chance = int((ft.kind[int(ft.level_start[level]):int(ft.level_start[level + 1])] == nat.KIND_CHANCE).sum())
+        chunks = -(-dt.desc.max_chance_children // 128)
+        w_off = 4 * n_chance * chunks * dt.ld
+        view = bufs.workspace[w_off:w_off + 4 * n_chance * dt.ld]
+        if self.world > 1:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        self.n_allreduce += 1
+
+    def _value_sweep(self, bufs, mask, with_br, algo, upd_p, modes):
+        tree, buf = C.byref(self.dtree.desc), C.byref(bufs.desc)
+
+        def levels(hi, lo, phase):
+            nat.call("prl_value_levels", tree, buf, mask, int(with_br), algo, upd_p, self.iter_counter, self.delay,
+                     nat.modes(*modes), hi, lo, phase, _stream())
+
+        hi = self.ft.n_levels - 1
+        for d in sorted(self._chance_levels, reverse=True):
+            if hi > d:
+                levels(hi, d + 1, 0)
+            levels(d, d, 1)
+            self._allreduce_chance_sums(bufs, d)
+            levels(d, d, 2)
+            hi = d - 1
+        if hi >= 0:
+            levels(hi, 0, 0)
+
+    def iteration(self, n=1):
+        tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
+        for _ in range(n):
+            for p in (0, 1):
+                self._value_sweep(self.bufs, 1 << p, False, self.algo, p, self.modes)
+                self.modes[p] = nat.STRAT_F32
+                nat.call("prl_reach_update", tree, buf, self.algo, p, self.iter_counter, self.delay, _stream())
+            self.iter_counter += 1
+
+    def exploitability_current(self):
+        self._value_sweep(self.bufs, 3, True, -1, -1, self.modes)
+        return self._metric(self.ops.root_exploitability())
+
+    def exploitability_average(self):
+        if self._eval_bufs is None:
+            self._eval_bufs = TreeBuffers(self.dtree, share=self.bufs)
+            self._eval_ops = TreeOps(self.dtree, self._eval_bufs)
+        m = self.average_modes()
+        self._eval_ops.reach_pass(m)
+        self._value_sweep(self._eval_bufs, 3, True, -1, -1, m)
+        return self._metric(self._eval_ops.root_exploitability())

@@ -315,7 +315,7 @@ class FlatTree:
         a warp of the GPU sweeps holds nodes of one kind; level_nonterm[d] = number of non-terminals of level d."""
         order = np.empty(self.n_nodes, np.int32)
         level_nonterm = np.zeros(self.n_levels, np.int64)
-        key = self.kind.astype(np.int64) * 4096 + self.n_children.astype(np.int64)
+        key = self.kind.astype(np.int64) * (1 << 32) + self.n_children.astype(np.int64)
         for d in range(self.n_levels):
             lo, hi = int(self.level_start[d]), int(self.level_start[d + 1])
             order[lo:hi] = lo + np.argsort(key[lo:hi], kind="stable")

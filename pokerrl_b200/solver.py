@@ -106,6 +106,9 @@ class DeviceTree:
         complete = np.nonzero((bc >= 0).sum(axis=1) == 5)[0]
         gs = torch.full((nb, self.R), -1, dtype=torch.int16, device=dev)
         ge, pos = torch.full_like(gs, -1), torch.full_like(gs, -1)
+        n_deck = rules.N_CARDS_IN_DECK
+        row_order = torch.full((nb, n_deck, n_deck - 1), -1, dtype=torch.int16, device=dev)
+        row_pos = torch.zeros((nb, self.R, 4), dtype=torch.uint8, device=dev)
         self.t_board_ranks = torch.full((nb, self.R), -1, dtype=torch.int32, device=dev)
         CH = 16384
         for i in range(0, complete.size, CH):
@@ -113,10 +116,14 @@ class DeviceTree:
             ranks = hand_rank_all_hands_on_given_boards(bc[complete[i:i + CH]], device=dev)
             self.t_board_ranks[ids] = ranks
             g1, g2, g3 = (torch.empty((ids.numel(), self.R), dtype=torch.int16, device=dev) for _ in range(3))
-            nat.call("prl_board_order_tables", C.c_void_p(ranks.data_ptr()), int(ids.numel()), self.R,
-                     C.c_void_p(g1.data_ptr()), C.c_void_p(g2.data_ptr()), C.c_void_p(g3.data_ptr()), _stream())
-            gs[ids], ge[ids], pos[ids] = g1, g2, g3
+            ro = torch.empty((ids.numel(), n_deck, n_deck - 1), dtype=torch.int16, device=dev)
+            rp = torch.zeros((ids.numel(), self.R, 4), dtype=torch.uint8, device=dev)
+            nat.call("prl_board_order_tables", C.c_void_p(ranks.data_ptr()), int(ids.numel()), self.R, n_deck,
+                     C.c_void_p(g1.data_ptr()), C.c_void_p(g2.data_ptr()), C.c_void_p(g3.data_ptr()),
+                     C.c_void_p(ro.data_ptr()), C.c_void_p(rp.data_ptr()), _stream())
+            gs[ids], ge[ids], pos[ids], row_order[ids], row_pos[ids] = g1, g2, g3, ro, rp
         self.t_board_gs, self.t_board_ge, self.t_board_pos = gs, ge, pos
+        self.t_board_row_order, self.t_board_row_pos = row_order, row_pos
         sp = ft.board_spec.sym_perm
         self.t_sym_perm = up(sp, np.int16) if sp is not None else None
         dec_per_level = [int(((ft.kind[int(ft.level_start[k]):int(ft.level_start[k + 1])] <= nat.KIND_P1)).sum())
@@ -130,6 +137,7 @@ class DeviceTree:
         d.board_mask, d.board_prob = self.t_board_mask.data_ptr(), self.t_board_prob.data_ptr()
         d.board_mult = self.t_board_mult.data_ptr()
         d.board_gs, d.board_ge, d.board_pos = gs.data_ptr(), ge.data_ptr(), pos.data_ptr()
+        d.board_row_order, d.board_row_pos = row_order.data_ptr(), row_pos.data_ptr()
         d.n_sym = 0 if sp is None else int(sp.shape[0])
         d.sym_perm = self.t_sym_perm.data_ptr() if sp is not None else None
         n_deck, n_hole = rules.N_CARDS_IN_DECK, rules.N_HOLE_CARDS
@@ -214,6 +222,7 @@ class CFRSolver:
 
     def __init__(self, ft, algo="CFRPlus", delay=0, device=None, avg_f64=False, persistent=True):
         self.persistent = bool(persistent)  # one cooperative launch per call instead of one launch per tree level
+        self.ft = ft
         self.algo_name = algo
         self.algo = ALGOS[algo]
         self.delay = int(delay) if algo == "CFRPlus" else 0

@@ -83,3 +83,27 @@ def test_suit_isomorphism_equals_full_enumeration():
         orc.iteration()
     a, b, c = s_full.exploitability_average(), s_iso.exploitability_average(), orc.exploitability_average()
     assert abs(a - c) <= 2e-5 * abs(c) and abs(b - c) <= 2e-5 * abs(c), (a, b, c)
+
+
+def test_sharded_schedule_single_rank_equals_plain_solver():
+    """The level-split sweep used for multi-GPU runs (world = 1: no communication) reproduces the plain solver."""
+    from pokerrl_b200.distributed import ShardedCFRSolver
+    from pokerrl_b200.game import games
+    from pokerrl_b200.solver import CFRSolver
+    spec = random_board_spec(20, 5)
+    ft = fhp_tree(spec)
+    g = games.Flop5Holdem
+    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=[1.0])
+    a, b = CFRSolver(ft, "CFRPlus"), ShardedCFRSolver(g, args, spec, "CFRPlus")
+    for _ in range(3):
+        a.iteration(1)
+        b.iteration(1)
+        assert a.exploitability_current() == b.exploitability_current()
+        assert a.exploitability_average() == b.exploitability_average()
+    assert torch_equal(a.bufs.regret, b.bufs.regret)
+    assert b.n_allreduce > 0
+
+
+def torch_equal(x, y):
+    import torch
+    return bool(torch.equal(x, y))
