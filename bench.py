@@ -1,23 +1,27 @@
 """Benchmark of the CFR hot path (BASELINE.json metric: CFR+ iterations/s, beside the CPU path on the same box).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload leduc_b5|leduc_pot|leduc_b3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload fhp|leduc_b5|leduc_b3|leduc_pot]
 
-A "step" = one full CFR+ iteration (both seats: value/regret sweep + reach/average sweep each) on the whole public
-tree, with the exact best-response evaluation of the current AND the average strategy every `--eval-every`
-iterations (BASELINE.json config 2: "exact BR every 20 iters"; evaluations fall inside the timed region).
-Default workload: DiscretizedNLLeduc with bet_sets.B_5, stack 20000 (873 586 nodes, 304 678 decision nodes,
-sum of actions 860 103, range 6) - the largest Leduc tree of SURVEY.md §6/§8(d), whose working set (~190 MB of node
-vectors + tables) exceeds the 126 MB L2.  The tree is deterministic: there is no dataset and no seed.
+A "step" = one full CFR+ iteration (both seats: value/regret sweep + reach/average sweep each) over the whole public
+tree, with the exact best-response evaluation of the current AND the average strategy every `--eval-every` iterations
+(inside the timed region).
 
-N > 1 (torchrun): the reference's `starting_stack_sizes` axis (`_CFRBase.py:44-69`: one independent tree per stack
-size, results averaged) is spread over the ranks - rank r solves stack 20000 + 1000 r - with no data-path
-collective ("weak" scaling); only the timing reduction uses NCCL.
+Default workload `fhp` (BASELINE.json configs[2], the game the metric is quoted on): Flop5Holdem (PokerRL/game/games.py:
+222-254) - full game, all C(52,5) = 2 598 960 boards as 134 459 suit-isomorphism classes, 1326-hand ranges, 2 016 890
+public nodes, 1 882 430 table rows; ~110 GB of HBM on one B200.  `leduc_b5` (configs[1]) = DiscretizedNLLeduc with
+bet_sets.B_5 (873 586 nodes, range 6).  The trees are deterministic: no dataset, no seed.
 
-Rank 0 prints ONE JSON line.  `--impl reference` times the CPU restatement of the reference's path (the C oracle,
-pinned bit-for-bit to the reference; /root/reference itself does not exist on the GPU box) on the same workload with
-all host threads.
+N > 1 (torchrun): fhp shards the boards over the ranks (strong scaling, one NCCL all-reduce of the chance-node sums per
+bottom-up sweep, pokerrl_b200/distributed.py); the Leduc workloads run one independent tree per rank (the reference's
+`starting_stack_sizes` axis, weak scaling, no data-path collective).
+
+Rank 0 prints ONE JSON line.  `--impl reference` times the CPU restatement of the reference's path on the host cores
+(/root/reference does not exist on the GPU box): the C oracle (OpenMP) for Leduc; for fhp - a game the reference cannot
+run at all (SURVEY.md headline 2) - the float64 numpy oracle on a bounded board sample, scaled to the full board count.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -26,54 +30,59 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "oracle")):
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-WORKLOADS = {
-    "leduc_b5": ("DiscretizedNLLeduc", "B_5"),
-    "leduc_b3": ("DiscretizedNLLeduc", "B_3"),
-    "leduc_pot": ("DiscretizedNLLeduc", "POT_ONLY"),
-}
+LEDUC = {"leduc_b5": "B_5", "leduc_b3": "B_3", "leduc_pot": "POT_ONLY"}
+WORKLOADS = ["fhp"] + list(LEDUC)
 
 
+# ---------------------------------------------------------------------------------------------------------- workloads
 def make_tree(workload, stack):
+    """Leduc workloads: (game class, FlatTree)"""
     from pokerrl_b200.game import bet_sets, games
     from pokerrl_b200.game.flat_tree import FlatTree
-    cn, bs = WORKLOADS[workload]
-    g = getattr(games, cn)
+    g = games.DiscretizedNLLeduc
     args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[stack, stack],
-                      bet_sizes_list_as_frac_of_pot=list(getattr(bet_sets, bs)))
+                      bet_sizes_list_as_frac_of_pot=list(getattr(bet_sets, LEDUC[workload])))
     return g, FlatTree(g, args)
+
+
+def fhp_args():
+    from pokerrl_b200.game import games
+    g = games.Flop5Holdem
+    return g, g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[g.DEFAULT_STACK_SIZE] * 2, bet_sizes_list_as_frac_of_pot=[1.0])
 
 
 def tree_stats(ft):
     import numpy as np
     dec = (ft.kind <= 1) & (ft.first_child >= 0)
     return dict(nodes=int(ft.n_nodes), decision=int(dec.sum()), sum_actions=int(ft.n_slots),
-                terminal=int((ft.kind >= 3).sum()), levels=int(ft.n_levels), range=int(ft.R),
+                terminal=int((ft.kind >= 3).sum()), fold=int((ft.kind == 3).sum()), showdown=int((ft.kind == 4).sum()),
+                levels=int(ft.n_levels), range=int(ft.R),
                 sum_actions_p=[int(ft.n_children[dec & (ft.kind == p)].sum()) for p in (0, 1)],
                 decision_p=[int((dec & (ft.kind == p)).sum()) for p in (0, 1)],
                 nonterminal=int(((ft.kind <= 2) & (ft.first_child >= 0)).sum()),
                 max_level_nodes=int(np.diff(ft.level_start).max()))
 
 
-def algorithmic_bytes(st):
-    """Minimum bytes the two sweeps of ONE seat must move in the level-synchronous design:
-    value sweep: write ev[p] (N rows) + read every child's ev[p] once (N-1) + opponent reach at terminals (T) +
-                 regret read/write and strategy read/write at the seat's decision nodes (4 rows per action) +
-                 structure (kind 1 B, first_child 4 B, n_children 4 B per node; pot/board/acted_last 9 B per
-                 terminal; first slot 4 B per decision node of the seat)
-    reach sweep: write reach[p] (N) + read each non-terminal parent row once (NT) + strategy read and average
-                 read/write at the seat's nodes (3 rows per action) + structure (parent 4 B, parent kind 1 B,
-                 slot 4 B, board 4 B per node)
-    Rows are range*4 bytes.  Returned per seat-averaged half-iteration: (value_bytes, reach_bytes)."""
+def algorithmic_bytes(st, two_card):
+    """Minimum bytes ONE seat's two sweeps must move in the level-synchronous design, rows = range*4 B.
+    value sweep: write ev[p] (N rows) + read every child's ev[p] once (N-1) + opponent reach at terminals (T) + regret
+                 read/write and strategy read/write at the seat's decision nodes (4 rows per action) + structure
+    reach sweep: write reach[p] (N) + read each non-terminal parent row once (NT) + strategy read and average read/write
+                 at the seat's nodes (3 rows per action) + structure
+    structure = per-node records (16 B record + 4 B work-list entry); two-card trees additionally read the per-board
+    strength tables at terminal rows: showdown 3 int16 + 4 uint8 per hand + 2 B x 52 x 51 card rows, fold the card rows.
+    Returned seat-averaged: (value_bytes, reach_bytes)."""
     row = st["range"] * 4
     N, T, NT = st["nodes"], st["terminal"], st["nonterminal"]
     sa = sum(st["sum_actions_p"]) / 2.0
-    dp = sum(st["decision_p"]) / 2.0
-    value = row * (N + (N - 1) + T + 4 * sa) + 9 * N + 9 * T + 4 * dp
-    reach = row * (N + NT + 3 * sa) + 13 * N
+    value = row * (N + (N - 1) + T + 4 * sa) + 20 * N
+    reach = row * (N + NT + 3 * sa) + 20 * N
+    if two_card:
+        value += st["showdown"] * (10 * st["range"] + 2 * 52 * 51) + st["fold"] * (2 * 52 * 51)
     return value, reach
 
 
@@ -100,7 +109,7 @@ class ClockSampler:
         self.proc.terminate()
         self.proc.wait()
         self.f.close()
-        sm, smax, reasons = [], None, set()
+        sm, smax, power, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             c = [x.strip() for x in line.split(",")]
@@ -109,6 +118,7 @@ class ClockSampler:
             try:
                 sm.append(float(c[1]))
                 smax = float(c[2])
+                power.append(float(c[3]))
             except ValueError:
                 continue
             for nme, v in zip(names, c[5:9]):
@@ -116,97 +126,141 @@ class ClockSampler:
                     reasons.add(nme)
         os.unlink(self.path)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def run_cpu(ft, n_iters, eval_every, threads):
-    """C-oracle CFR+ on the host: returns seconds per iteration (including the evaluation cadence)."""
+# ---------------------------------------------------------------------------------------------------------- CPU arms
+def run_cpu_leduc(ft, n_iters, eval_every, threads):
+    """C-oracle CFR+ on the host: seconds per iteration (including the evaluation cadence)."""
     import cfr_c
     s = cfr_c.OracleCSolver(ft, "CFRPlus", avg_f64=False, n_threads=threads)
-    s.iteration(1)  # warm the caches / page in
+    s.iteration(1)
     t0 = time.perf_counter()
     for i in range(n_iters):
         s.iteration(1)
         if (i + 1) % eval_every == 0:
             s.exploitability_current()
             s.exploitability_average()
-    dt = time.perf_counter() - t0
-    return dt / n_iters, s.n_threads
+    return (time.perf_counter() - t0) / n_iters, s.n_threads
+
+
+def run_cpu_fhp(n_boards_sample, n_iters, n_boards_full):
+    """float64 numpy oracle (oracle/cfr2_numpy.py) on a sample of boards; returns (seconds per FULL-GAME iteration
+    extrapolated linearly in the number of boards, seconds per sampled iteration, boards sampled, BLAS threads)."""
+    import cfr2_numpy as o2
+    from twocard_common import fhp_tree, oracle_tree, random_board_spec
+    ft = fhp_tree(random_board_spec(n_boards_sample, 123))
+    nb = ft.board_spec.boards.shape[0]
+    c = o2.Oracle2CFR(oracle_tree(ft), "CFRPlus", ev_normalizer=ft.game_cls.EV_NORMALIZER)
+    c.iteration()  # builds and caches the per-board sign matrices (one-off in a real solver as well)
+    t0 = time.perf_counter()
+    for _ in range(n_iters):
+        c.iteration()
+    sec = (time.perf_counter() - t0) / n_iters
+    threads = 1
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        pass
+    return sec * n_boards_full / nb, sec, nb, threads
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="leduc_b5", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="fhp", choices=WORKLOADS)
     ap.add_argument("--eval-every", type=int, default=20)
+    ap.add_argument("--fhp-boards", type=int, default=0, help="debug: only the first n isomorphism classes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    W = max(3, a.warmup)
-    K = a.steps
-    stack = 20000 + 1000 * rank
-    cfg = {"workload": "%s CFR+ delay 0, %s, stack 20000%s, exact BR (current+average) every %d iterations" % (
-        WORKLOADS[a.workload][0], "bet_sets." + WORKLOADS[a.workload][1],
-        " + 1000*rank (one tree per rank)" if world > 1 else "", a.eval_every)}
+    fhp = a.workload == "fhp"
+    K = a.steps if a.steps is not None else (40 if fhp else 2000)
+    W = max(3, a.warmup if a.warmup is not None else (3 if fhp else 20))
+    N_CLASSES = 134459
+    if fhp:
+        cfg = {"workload": "Flop5Holdem CFR+ delay 0, full game: 134 459 suit-isomorphism classes of the 2 598 960 "
+                           "five-card boards, range 1326, stack 20000, exact BR (current+average) every %d iterations"
+                           % a.eval_every}
+    else:
+        cfg = {"workload": "DiscretizedNLLeduc CFR+ delay 0, bet_sets.%s, stack 20000%s, exact BR (current+average) "
+                           "every %d iterations" % (LEDUC[a.workload], " + 1000*rank (one tree per rank)" if world > 1 else "",
+                                                    a.eval_every)}
 
     # ------------------------------------------------------------------ reference arm (CPU restatement)
     if a.impl == "reference":
         if rank != 0:
             return
-        g, ft = make_tree(a.workload, 20000)
-        st = tree_stats(ft)
         ncpu = os.cpu_count() or 1
-        K = min(K, 200)
-        sec, threads = run_cpu(ft, K, a.eval_every, min(ncpu, 16))
-        cfg.update(tree=st)
-        v = 1.0 / sec
+        if fhp:
+            K = min(K, 10)
+            full_sec, sec, nb, threads = run_cpu_fhp(32, K, N_CLASSES)
+            v = 1.0 / full_sec
+            sample = ("%d CFR+ iterations of oracle/cfr2_numpy.py (float64 numpy, dense 1326x1326 sign-matrix showdowns) "
+                      "on %d random boards: %.3f s/iteration, extrapolated linearly to the %d board classes of the full "
+                      "game; the reference itself cannot run Hold'em trees" % (K, nb, sec, N_CLASSES))
+            ms = full_sec * 1e3
+        else:
+            g, ft = make_tree(a.workload, 20000)
+            K = min(K, 200)
+            sec, threads = run_cpu_leduc(ft, K, a.eval_every, min(ncpu, 16))
+            cfg.update(tree=tree_stats(ft))
+            v, ms = 1.0 / sec, sec * 1e3
+            sample = "%d full CFR+ iterations of the same tree by oracle/cfr_oracle.c (OpenMP)" % K
         print(json.dumps({
             "impl": "reference", "metric": "CFR+ iterations/s", "value": v, "unit": "iterations/s", "n_gpus": a.gpus,
-            "steps": K, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic (deterministic game tree, no dataset)",
-            "config": cfg,
-            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port",
-                             "sample": "%d full CFR+ iterations of the same tree by oracle/cfr_oracle.c (OpenMP)" % K},
+            "steps": K, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if fhp else "weak", "vs_baseline": None, "dtype": "f64" if fhp else "f32",
+            "data": "synthetic (deterministic game tree, no dataset)", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
 
     # ------------------------------------------------------------------ B200 arm
-    import ctypes as C
-
     import torch
     import torch.distributed as dist
     from pokerrl_b200 import _native as nat
-    from pokerrl_b200.solver import CFRSolver, _stream
+    from pokerrl_b200.solver import CFRSolver
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = "cuda:%d" % local_rank
     t0 = time.perf_counter()
-    g, ft = make_tree(a.workload, stack)
-    t_build = time.perf_counter() - t0
-    st = tree_stats(ft)
-    t0 = time.perf_counter()
-    s = CFRSolver(ft, "CFRPlus", delay=0, avg_f64=False)
+    spec = None
+    if fhp:
+        from pokerrl_b200.distributed import ShardedCFRSolver
+        from pokerrl_b200.game.holdem_boards import BoardSpec
+        g, args = fhp_args()
+        spec = BoardSpec.full_game(g.RULES)
+        if a.fhp_boards:
+            spec = BoardSpec(spec.boards[:a.fhp_boards], spec.board_prob[:a.fhp_boards], spec.board_mult[:a.fhp_boards],
+                             spec.sym_perm, "first %d classes (debug)" % a.fhp_boards)
+            cfg["workload"] += " [DEBUG SUBSET: %d classes]" % a.fhp_boards
+        t_build = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        s = ShardedCFRSolver(g, args, spec, "CFRPlus", device=dev, rank=rank, world=world)
+        ft = s.ft
+    else:
+        g, ft = make_tree(a.workload, 20000 + 1000 * rank)
+        t_build = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        s = CFRSolver(ft, "CFRPlus", delay=0, avg_f64=False, device=dev)
     torch.cuda.synchronize()
     t_upload = time.perf_counter() - t0
-    tree_bytes = sum(getattr(s.dtree, k).numel() * getattr(s.dtree, k).element_size()
-                     for k in ("t_parent", "t_first_child", "t_n_children", "t_slot", "t_kind", "t_acted_last",
-                               "t_pot", "t_board"))
-
-    def step(i):
-        s.iteration(1)
-        if (i + 1) % a.eval_every == 0:
-            return s.exploitability_current(), s.exploitability_average()
-        return None
+    st = tree_stats(ft)
+    tree_bytes = sum(t.numel() * t.element_size() for k, t in vars(s.dtree).items()
+                     if k.startswith("t_") and isinstance(t, torch.Tensor))
 
     def steps(i0, n):
-        """n steps starting at step index i0; iterations between two evaluations share one persistent launch"""
+        """n steps starting at step index i0; iterations between two evaluations share one call"""
         out, i = [], i0
         while i < i0 + n:
             m = min(a.eval_every - (i % a.eval_every), i0 + n - i)
@@ -216,28 +270,25 @@ def main():
                 out.append((i, s.exploitability_current(), s.exploitability_average()))
         return out
 
-    for i in range(W):
-        step(i)
-    s.reset()  # timed run starts from iteration 0 so that the exploitability trace is the reference's
-    for i in range(W):
-        step(i)
+    steps(0, W)
+    s.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.5)  # let nvidia-smi start sampling while the GPU runs untimed steps
+    steps(0, W)
     s.reset()
     torch.cuda.synchronize()
 
-    # --- timed region: K steps, device-timed with CUDA events on the launching stream
+    # --- timed region: K steps, device-timed with CUDA events on the launching stream, barrier + sync on both sides
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler is not None:
-        time.sleep(0.5)  # let nvidia-smi start sampling; the GPU is kept busy by an untimed step stream meanwhile
-        for i in range(W):
-            s.iteration(1)
-        s.reset()
-        torch.cuda.synchronize()
     launches0 = nat.lib().prl_launch_count()
+    n_ar0 = getattr(s, "n_allreduce", 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    trace = []
     wall0 = time.perf_counter()
     ev0.record()
     trace = steps(0, K)
@@ -252,21 +303,77 @@ def main():
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms = float(t.item())
+    n_allreduce = getattr(s, "n_allreduce", 0) - n_ar0
 
-    # --- e2e: the user-facing call (CFRPlus façade: iteration + logging through ChiefBase, results read on host)
+    # --- roofline of the dominant kernels, timed live with CUDA events on their stream (sweep by sweep, after the run)
+    import ctypes as C
+    from pokerrl_b200.solver import _stream
+    vb, rb = algorithmic_bytes(st, fhp)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    psrc = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    if fhp:
+        tree_p, buf_p = C.byref(s.dtree.desc), C.byref(s.bufs.desc)
+        v_ms, r_ms = [], []
+        for rep in range(4):
+            for p in (0, 1):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record()
+                s._value_sweep(s.bufs, 1 << p, False, s.algo, p, s.modes)
+                e[1].record()
+                nat.call("prl_reach_update", tree_p, buf_p, s.algo, p, s.iter_counter, s.delay, _stream())
+                e[2].record()
+                torch.cuda.synchronize()
+                if rep >= 1:
+                    v_ms.append(e[0].elapsed_time(e[1]))
+                    r_ms.append(e[1].elapsed_time(e[2]))
+            s.iter_counter += 1
+        vm, rm = statistics.mean(v_ms), statistics.mean(r_ms)
+        achieved = vb / (vm * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "value/regret sweep of one seat = terminal2_kernel + value2_kernel<false,true> + "
+                    "chance_*_kernel over all %d levels (terminal2_kernel is the largest share, see profiles/)" % st["levels"],
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": psrc,
+                    "algorithmic_bytes_per_sweep": vb, "sweep_ms": vm, "traffic": None,
+                    "reach_sweep": {"kernel": "reach2_kernel<true> x %d levels" % st["levels"], "algorithmic_bytes": rb,
+                                    "sweep_ms": rm, "achieved": rb / (rm * 1e-3) / 1e9, "frac": rb / (rm * 1e-3) / 1e9 / peak}}
+    else:
+        it_ms = []
+        for rep in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s.iteration(a.eval_every)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep >= 2:
+                it_ms.append(e0.elapsed_time(e1))
+        l_ms = statistics.mean(it_ms)
+        bpl = a.eval_every * 2 * (vb + rb)
+        achieved = bpl / (l_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "cfr_iterations_kernel<6,2> (persistent cooperative kernel: %d CFR+ iterations "
+                    "= %d level steps with grid barriers per launch)" % (a.eval_every, a.eval_every * 2 * (2 * st["levels"] - 1)),
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": psrc,
+                    "algorithmic_bytes_per_launch": bpl, "launch_ms": l_ms, "traffic": None,
+                    "note": "latency/occupancy-bound, not HBM-bound: R = 6 rows, 27 dependent level steps per seat"}
+
+    # --- e2e: the user-facing call (CFRPlus façade: iteration() + logging through ChiefBase, results read on the host)
     from pokerrl_b200.cfr.CFRPlus import CFRPlus
     from pokerrl_b200.game import bet_sets, games
     from pokerrl_b200.rl.base_cls.workers.ChiefBase import ChiefBase
     del s
     torch.cuda.empty_cache()
-    cn, bs = WORKLOADS[a.workload]
     chief = ChiefBase(t_prof=None)
-    import contextlib
-    import io
     with contextlib.redirect_stdout(io.StringIO()):
-        cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=getattr(games, cn),
-                      agent_bet_set=list(getattr(bet_sets, bs)), starting_stack_sizes=[stack], delay=0,
-                      eval_every=a.eval_every)
+        if fhp:
+            cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=games.Flop5Holdem, agent_bet_set=[1.0], delay=0,
+                          eval_every=a.eval_every, device=dev, board_spec=spec)
+        else:
+            cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=games.DiscretizedNLLeduc,
+                          agent_bet_set=list(getattr(bet_sets, LEDUC[a.workload])),
+                          starting_stack_sizes=[20000 + 1000 * rank], delay=0, eval_every=a.eval_every, device=dev)
     for _ in range(W):
         cfr.iteration()
     cfr.reset()
@@ -282,56 +389,30 @@ def main():
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_s = float(t2.item())
-    n_evals = K // a.eval_every
-    d2h_per_step = 2 * 8 * n_evals / K  # two float32[2] exploitability read-backs per evaluation
-
-    # --- roofline of the dominant kernel: the persistent cooperative kernel that runs whole CFR+ iterations
-    # (cfr_iterations_kernel, one launch per `eval_every` iterations), timed live with CUDA events on its stream
-    s = cfr.solvers[0]
-    it_ms = []
-    for rep in range(12):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        s.iteration(a.eval_every)
-        e1.record()
-        torch.cuda.synchronize()
-        if rep >= 2:
-            it_ms.append(e0.elapsed_time(e1))
-    vb, rb = algorithmic_bytes(st)
-    bytes_per_launch = a.eval_every * 2 * (vb + rb)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    l_ms = statistics.mean(it_ms)
-    achieved = bytes_per_launch / (l_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "cfr_iterations_kernel<6,2> (persistent cooperative kernel: %d CFR+ iterations = "
-                "%d level steps with grid barriers per launch)" % (a.eval_every, a.eval_every * 2 * (2 * st["levels"] - 1)),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": l_ms,
-                "algorithmic_bytes_per_iteration": 2 * (vb + rb), "traffic": None,
-                "note": "latency/occupancy-bound, not HBM-bound: R = 6 rows, 27 dependent level steps per seat"}
+    d2h_per_step = 2 * 8 * (K // a.eval_every) / K  # two float32[2] exploitability read-backs per evaluation
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    jobs = 1 if fhp else world  # fhp: ONE game sharded over the ranks; Leduc: one tree per rank
     out = {
-        "metric": "CFR+ iterations/s", "value": world * K / (max_ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (deterministic game tree, no dataset)",
-        "config": dict(cfg, tree=st, l2="working set > L2: node vectors %d MB + tables %d MB + structure %d MB; no explicit flush" % (
-            4 * st["nodes"] * st["range"] * 4 // 2 ** 20, 3 * st["sum_actions"] * st["range"] * 4 // 2 ** 20,
-            tree_bytes // 2 ** 20), parallelism="one tree per rank (stack-size axis), no collective"),
+        "metric": "CFR+ iterations/s", "value": jobs * K / (max_ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True,
+        "scaling": "strong" if fhp else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (deterministic game tree, no dataset)",
+        "config": dict(cfg, tree_per_rank=st,
+                       l2="per-rank working set %.1f GB >> 126 MB L2 (no explicit flush)" % (
+                           (6 * st["nodes"] + 3 * st["sum_actions"]) * st["range"] * 4 / 2 ** 30),
+                       parallelism=("boards sharded over %d ranks, one NCCL all-reduce of the chance-node sums per bottom-up "
+                                    "sweep (%d in the timed region)" % (world, n_allreduce)) if fhp
+                       else "one tree per rank (stack-size axis), no collective"),
         "clocks": clocks,
-        "e2e": {"value": world * K / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 0,
+        "e2e": {"value": jobs * K / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": d2h_per_step,
-                "note": "CFRPlus.iteration() façade incl. ChiefBase logging; CFR has no per-step host input - the "
-                        "one-off tree upload is reported under setup"},
-        "setup": {"tree_build_s": t_build, "tree_upload_s": t_upload, "tree_h2d_bytes": tree_bytes},
+                "note": "CFRPlus.iteration() facade incl. ChiefBase logging; CFR has no per-step host input - the one-off "
+                        "tree / board-table upload is reported under setup"},
+        "setup": {"tree_build_s": t_build, "upload_and_tables_s": t_upload, "tree_h2d_bytes": int(tree_bytes)},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall * 1e3 / K,
         "exploitability_trace_mbb_per_g": trace[-3:],
@@ -339,15 +420,20 @@ def main():
     }
     if world == 1 and not a.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
-        per_iter_guess = 0.25 * st["nodes"] / 873586.0
-        n = max(2, min(K, int(15.0 / max(per_iter_guess, 1e-4))))
-        n = (n // a.eval_every) * a.eval_every or n
-        _, ft0 = (g, ft)
-        sec, threads = run_cpu(ft0, n, a.eval_every, min(ncpu, 16))
-        out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "iterations/s", "cores": threads, "kind": "port",
-                               "sample": "%d full CFR+ iterations (same tree, same BR cadence) by oracle/cfr_oracle.c "
-                                         "with OpenMP; the reference's own Python path is ~400x slower per node "
-                                         "(BASELINE.md: 0.448 s/iter on the 1 096-node tree)" % n}
+        if fhp:
+            full_sec, sec, nb, threads = run_cpu_fhp(32, 10, N_CLASSES)
+            out["cpu_baseline"] = {"value": 1.0 / full_sec, "unit": "iterations/s", "cores": threads, "kind": "port",
+                                   "sample": "10 CFR+ iterations of oracle/cfr2_numpy.py (float64 numpy) on %d random "
+                                             "boards at %.3f s/iteration, extrapolated linearly to 134 459 board classes; "
+                                             "the reference cannot run Hold'em trees at all (SURVEY.md headline 2)" % (nb, sec)}
+        else:
+            n = max(2, min(K, int(15.0 / max(0.014 * st["nodes"] / 873586.0, 1e-4))))
+            n = (n // a.eval_every) * a.eval_every or n
+            sec, threads = run_cpu_leduc(ft, n, a.eval_every, min(ncpu, 16))
+            out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "iterations/s", "cores": threads, "kind": "port",
+                                   "sample": "%d full CFR+ iterations (same tree, same BR cadence) by oracle/cfr_oracle.c "
+                                             "with OpenMP; the reference's own Python path is ~400x slower per node "
+                                             "(BASELINE.md: 0.448 s/iter on the 1 096-node tree)" % n}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

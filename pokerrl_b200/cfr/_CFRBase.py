@@ -21,7 +21,7 @@ class CFRBase:
     _SOLVER_ALGO = None  # "VanillaCFR" | "CFRPlus" | "LinearCFR"
 
     def __init__(self, name, chief_handle, game_cls, agent_bet_set, algo_name, starting_stack_sizes=None,
-                 delay=0, eval_every=1, device=None, avg_f64=False):
+                 delay=0, eval_every=1, device=None, avg_f64=False, board_spec=None):
         self._name = name
         self._n_seats = 2
         self._chief_handle = chief_handle
@@ -34,9 +34,8 @@ class CFRBase:
             for s in self._starting_stack_sizes]
         env_cls = get_env_cls_from_str(self._game_cls_str)
         self._env_bldrs = [HistoryEnvBuilder(env_cls=env_cls, env_args=a) for a in self._env_args]
-        self._flat_trees = [FlatTree(env_cls, a) for a in self._env_args]
-        self._solvers = [CFRSolver(ft, algo=self._SOLVER_ALGO, delay=delay, device=device, avg_f64=avg_f64)
-                         for ft in self._flat_trees]
+        self._solvers = [self._make_solver(env_cls, a, delay, device, avg_f64, board_spec) for a in self._env_args]
+        self._flat_trees = [s.ft for s in self._solvers]
         for ft, a in zip(self._flat_trees, self._env_args):
             print("Tree with stack size", a.starting_stack_sizes_list, "has", ft.n_nodes - 1,
                   "nodes out of which", ft.n_nonterm - 1, "are non-terminal.")
@@ -50,6 +49,19 @@ class CFRBase:
         self._exp_all_averaged_curr_total = ch.create_experiment(self._name + "_Curr_total_averaged_" + algo_name)
         self._exp_all_averaged_avg_total = ch.create_experiment(self._name + "_Avg_total_averaged_" + algo_name)
         self._iter_counter = None
+
+    def _make_solver(self, env_cls, env_args, delay, device, avg_f64, board_spec):
+        """One engine per stack size.  Two-card games launched under torch.distributed (one process per GPU) shard their
+        boards over the ranks (pokerrl_b200.distributed); everything else runs on this process's GPU."""
+        import torch.distributed as dist
+        if env_cls.RULES.N_HOLE_CARDS == 2 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from pokerrl_b200.distributed import ShardedCFRSolver
+            from pokerrl_b200.game.holdem_boards import BoardSpec
+            spec = board_spec if board_spec is not None else BoardSpec.full_game(env_cls.RULES)
+            return ShardedCFRSolver(env_cls, env_args, spec, algo=self._SOLVER_ALGO, delay=delay, device=device,
+                                    rank=dist.get_rank(), world=dist.get_world_size())
+        ft = FlatTree(env_cls, env_args, board_spec=board_spec)
+        return CFRSolver(ft, algo=self._SOLVER_ALGO, delay=delay, device=device, avg_f64=avg_f64)
 
     name = property(lambda s: s._name)
     algo_name = property(lambda s: s._algo_name)

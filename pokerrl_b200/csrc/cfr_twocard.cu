@@ -22,7 +22,8 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kTermThreads = 512;
+constexpr int kVecThreads = 128;  // row kernels: 128 threads x 4 hands
+constexpr int kTermThreads = 256;
 constexpr int kRowStride = 53;     // n_deck - 1 hands per card row + 1, +1 padding against bank conflicts
 constexpr int kChanceChunk = 128;  // children summed per block in the first stage of a chance-node reduction
 
@@ -33,23 +34,48 @@ struct Ctx2 {
     int mask;        // seats to process
     int mode[2];     // strategy source per seat
     int algo, upd_p, iter, delay;
+    float m_old, m_new;  // CFR+ averaging weights of this iteration (CFRPlus.py:68-73), computed on the host
 };
 
 __device__ __forceinline__ const float* strat_table(const Ctx2& c, int m) {
     return (m == PRL_STRAT_F32) ? c.B.strat : (const float*)c.B.avg;
 }
 
-// probability of the action leading to the child in row `slot` (rows fs..fs+A-1 belong to one decision node)
-__device__ __forceinline__ float strat_value(const Ctx2& c, int m, int slot, int fs, int A, int h) {
+// ---- four hands per thread: rows are read / written as float4 (ld is a multiple of 4, rows are 16-byte aligned) -------
+struct F4 {
+    float v[4];
+};
+__device__ __forceinline__ F4 ld4(const float* p) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    return F4{{q.x, q.y, q.z, q.w}};
+}
+__device__ __forceinline__ void st4(float* p, const F4& a) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ F4 splat(float x) { return F4{{x, x, x, x}}; }
+
+// probabilities of the action leading to the child in table row `slot` for hands h0..h0+3 (rows fs..fs+A-1 belong to
+// one decision node)
+__device__ __forceinline__ F4 strat4(const Ctx2& c, int m, int slot, int fs, int A, int h0) {
     const size_t ld = c.T.ld;
-    if (m == PRL_STRAT_UNIFORM64) return 1.0f / (float)A;
+    if (m == PRL_STRAT_UNIFORM64) return splat(1.0f / (float)A);
     if (m == PRL_STRAT_AVG_SUM) {  // reach-weighted sums, normalised on the fly (LinearCFR.py:64-71)
         const float* tab = (const float*)c.B.avg;
-        float tot = 0.0f;
-        for (int j = 0; j < A; ++j) tot += tab[(size_t)(fs + j) * ld + h];
-        return (tot == 0.0f) ? 1.0f / (float)A : tab[(size_t)slot * ld + h] / tot;
+        F4 tot = splat(0.0f), mine = splat(0.0f);
+        for (int j = 0; j < A; ++j) {
+            const F4 x = ld4(tab + (size_t)(fs + j) * ld + h0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tot.v[i] += x.v[i];
+                if (fs + j == slot) mine.v[i] = x.v[i];
+            }
+        }
+        F4 s;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s.v[i] = (tot.v[i] == 0.0f) ? 1.0f / (float)A : mine.v[i] / tot.v[i];
+        return s;
     }
-    return strat_table(c, m)[(size_t)slot * ld + h];
+    return ld4(strat_table(c, m) + (size_t)slot * ld + h0);
 }
 
 __device__ __forceinline__ bool hand_blocked(const prl_tree_t& T, int h, unsigned long long bmask) {
@@ -58,67 +84,72 @@ __device__ __forceinline__ bool hand_blocked(const prl_tree_t& T, int h, unsigne
 }
 
 // ------------------------------------------------------------------------------------------------ reach (top-down)
-// thread = (child node n of the level, hand h); StrategyFiller.py:118-146 generalised
+// block x = child node n of the level, thread = four hands; StrategyFiller.py:118-146 generalised
 template <bool UPDATE_AVG>
-__global__ void __launch_bounds__(kThreads) reach2_kernel(const Ctx2 c) {
-    const int ld = c.T.ld;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = c.lo + (int)(idx / ld);
-    const int h = (int)(idx % ld);
-    if (n >= c.lo + c.n || h >= c.T.n_range) return;
+__global__ void __launch_bounds__(kVecThreads) reach2_kernel(const Ctx2 c) {
+    const int ld = c.T.ld, R = c.T.n_range;
+    const int n = c.lo + blockIdx.x;
+    const int h0 = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (h0 >= R) return;
     const size_t N = (size_t)c.T.n_nodes;
     const int par = c.T.parent[n];
 #pragma unroll 1
     for (int q = 0; q < 2; ++q) {
         if (!(c.mask & (1 << q))) continue;
         float* reach_q = c.B.reach + (size_t)q * N * ld;
-        float r;
+        F4 r;
         if (par < 0) {
-            r = 1.0f / (float)c.T.n_range;  // PublicTree.py:122-124
+            r = splat(1.0f / (float)R);  // PublicTree.py:122-124
         } else {
-            const float rp = reach_q[(size_t)par * ld + h];
+            const F4 rp = ld4(reach_q + (size_t)par * ld + h0);
             const int pk = c.T.kind[par];
             if (pk == PRL_KIND_CHANCE) {  // the deal multiplies both rows and zeroes hands holding a board card
                 const int b = c.T.board[n];
-                r = hand_blocked(c.T, h, c.T.board_mask[b]) ? 0.0f : rp * c.T.board_prob[b];
+                const unsigned long long bm = c.T.board_mask[b];
+                const float pr = c.T.board_prob[b];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r.v[i] = (h0 + i < R && !hand_blocked(c.T, h0 + i, bm)) ? rp.v[i] * pr : 0.0f;
             } else if (pk == q) {
                 const int slot = c.T.slot[n];
                 const int m = c.mode[q];
                 const int fs = c.T.slot[c.T.first_child[par]];
-                const float s = strat_value(c, m, slot, fs, c.T.n_children[par], h);
-                r = s * rp;
+                const F4 s = strat4(c, m, slot, fs, c.T.n_children[par], h0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r.v[i] = s.v[i] * rp.v[i];
                 if (UPDATE_AVG && q == c.upd_p) {
-                    float* a = (float*)c.B.avg + (size_t)slot * ld + h;
+                    float* ap = (float*)c.B.avg + (size_t)slot * ld + h0;
                     if (c.algo == PRL_ALGO_CFR_PLUS) {  // CFRPlus.py:65-87 (float table)
                         if (c.iter >= c.delay) {
-                            const double cw = 0.5 * ((double)c.iter * (c.iter + 1) - (double)c.delay * (c.delay + 1));
-                            const double nw = (double)c.iter - c.delay + 1;
-                            *a = (float)(cw / (cw + nw)) * (*a) + (float)(nw / (cw + nw)) * s;
+                            F4 a = ld4(ap);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) a.v[i] = c.m_old * a.v[i] + c.m_new * s.v[i];
+                            st4(ap, a);
                         }
-                    } else if (c.algo == PRL_ALGO_LINEAR) {
-                        *a = *a + r * (float)(c.iter + 1);  // LinearCFR.py:56-61
                     } else {
-                        *a = *a + r;  // VanillaCFR.py:57-62
+                        F4 a = ld4(ap);
+                        const float w = (c.algo == PRL_ALGO_LINEAR) ? (float)(c.iter + 1) : 1.0f;  // LinearCFR.py:56-61
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a.v[i] = a.v[i] + r.v[i] * w;  // VanillaCFR.py:57-62
+                        st4(ap, a);
                     }
                 }
             } else {
                 r = rp;
             }
         }
-        reach_q[(size_t)n * ld + h] = r;
+        st4(reach_q + (size_t)n * ld + h0, r);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ decision nodes (bottom-up)
-// thread = (work-list entry t -> decision node n, hand h); ValueFiller.py:80-93 + _CFRBase.py:146-185 + regret matching
+// block x = work-list entry t -> decision node n, thread = four hands; ValueFiller.py:80-93 + _CFRBase.py:146-185 +
+// regret matching
 template <bool WITH_BR, bool UPDATE>
-__global__ void __launch_bounds__(kThreads) value2_kernel(const Ctx2 c) {
+__global__ void __launch_bounds__(kVecThreads) value2_kernel(const Ctx2 c) {
     const int ld = c.T.ld;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = (int)(idx / ld);
-    const int h = (int)(idx % ld);
-    if (t >= c.n || h >= c.T.n_range) return;
-    const int n = c.T.order[c.lo + t];
+    const int h0 = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (h0 >= c.T.n_range) return;
+    const int n = c.T.order[c.lo + blockIdx.x];
     const size_t N = (size_t)c.T.n_nodes;
     const int kind = c.T.kind[n], fc = c.T.first_child[n], A = c.T.n_children[n];
     const int fs = c.T.slot[fc];
@@ -127,41 +158,77 @@ __global__ void __launch_bounds__(kThreads) value2_kernel(const Ctx2 c) {
         if (!(c.mask & (1 << p))) continue;
         float* ev_p = c.B.ev + (size_t)p * N * ld;
         float* evbr_p = WITH_BR ? c.B.ev_br + (size_t)p * N * ld : nullptr;
-        const float* ecol = ev_p + (size_t)fc * ld + h;
-        float v = 0.0f, vbr = 0.0f;
+        const float* ecol = ev_p + (size_t)fc * ld + h0;
+        F4 v = splat(0.0f), vbr = splat(0.0f);
         if (kind != p) {  // the other seat acts: sums over children
-            for (int k = 0; k < A; ++k) v += ecol[(size_t)k * ld];
+            for (int k = 0; k < A; ++k) {
+                const F4 e = ld4(ecol + (size_t)k * ld);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v.v[i] += e.v[i];
+            }
             if (WITH_BR)
-                for (int k = 0; k < A; ++k) vbr += evbr_p[(size_t)(fc + k) * ld + h];
+                for (int k = 0; k < A; ++k) {
+                    const F4 e = ld4(evbr_p + (size_t)(fc + k) * ld + h0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vbr.v[i] += e.v[i];
+                }
         } else {
             const int m = c.mode[p];
-            for (int k = 0; k < A; ++k) v += strat_value(c, m, fs + k, fs, A, h) * ecol[(size_t)k * ld];
+            for (int k = 0; k < A; ++k) {
+                const F4 e = ld4(ecol + (size_t)k * ld);
+                const F4 s = strat4(c, m, fs + k, fs, A, h0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v.v[i] += s.v[i] * e.v[i];
+            }
             if (WITH_BR) {
-                vbr = evbr_p[(size_t)fc * ld + h];
-                for (int k = 1; k < A; ++k) vbr = fmaxf(vbr, evbr_p[(size_t)(fc + k) * ld + h]);
+                vbr = ld4(evbr_p + (size_t)fc * ld + h0);
+                for (int k = 1; k < A; ++k) {
+                    const F4 e = ld4(evbr_p + (size_t)(fc + k) * ld + h0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vbr.v[i] = fmaxf(vbr.v[i], e.v[i]);
+                }
             }
             if (UPDATE && p == c.upd_p) {
-                float* rcol = c.B.regret + (size_t)fs * ld + h;
-                float* scol = c.B.strat + (size_t)fs * ld + h;
+                float* rcol = c.B.regret + (size_t)fs * ld + h0;
+                float* scol = c.B.strat + (size_t)fs * ld + h0;
                 const float w = (float)(c.iter + 1);
-                float ssum = 0.0f;
-                for (int k = 0; k < A; ++k) {
-                    const float d = ecol[(size_t)k * ld] - v;
-                    float r;
-                    if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rcol[(size_t)k * ld], 0.0f);
-                    else if (c.algo == PRL_ALGO_LINEAR) r = w * d + rcol[(size_t)k * ld];
-                    else r = d + rcol[(size_t)k * ld];
-                    rcol[(size_t)k * ld] = r;
-                    ssum += fmaxf(r, 0.0f);
+                F4 ssum = splat(0.0f);
+                for (int k = 0; k < A; ++k) {  // pass A: positive regret mass (new regrets are recomputed in pass B)
+                    const F4 e = ld4(ecol + (size_t)k * ld), rg = ld4(rcol + (size_t)k * ld);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float d = e.v[i] - v.v[i];
+                        float r;
+                        if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rg.v[i], 0.0f);
+                        else if (c.algo == PRL_ALGO_LINEAR) r = w * d + rg.v[i];
+                        else r = d + rg.v[i];
+                        ssum.v[i] += fmaxf(r, 0.0f);
+                    }
                 }
                 const float uni = 1.0f / (float)A;
-                const float inv = (ssum > 0.0f) ? 1.0f / ssum : 0.0f;
-                for (int k = 0; k < A; ++k)
-                    scol[(size_t)k * ld] = (ssum > 0.0f) ? fmaxf(rcol[(size_t)k * ld], 0.0f) * inv : uni;
+                F4 inv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) inv.v[i] = (ssum.v[i] > 0.0f) ? 1.0f / ssum.v[i] : 0.0f;
+                for (int k = 0; k < A; ++k) {  // pass B: store regrets and the regret-matching strategy
+                    const F4 e = ld4(ecol + (size_t)k * ld);
+                    F4 rg = ld4(rcol + (size_t)k * ld), st;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float d = e.v[i] - v.v[i];
+                        float r;
+                        if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rg.v[i], 0.0f);
+                        else if (c.algo == PRL_ALGO_LINEAR) r = w * d + rg.v[i];
+                        else r = d + rg.v[i];
+                        rg.v[i] = r;
+                        st.v[i] = (ssum.v[i] > 0.0f) ? fmaxf(r, 0.0f) * inv.v[i] : uni;
+                    }
+                    st4(rcol + (size_t)k * ld, rg);
+                    st4(scol + (size_t)k * ld, st);
+                }
             }
         }
-        ev_p[(size_t)n * ld + h] = v;
-        if (WITH_BR) evbr_p[(size_t)n * ld + h] = vbr;
+        st4(ev_p + (size_t)n * ld + h0, v);
+        if (WITH_BR) st4(evbr_p + (size_t)n * ld + h0, vbr);
     }
 }
 
@@ -468,6 +535,14 @@ __global__ void root_exploitability2_kernel(prl_tree_t T, prl_buffers_t B, float
     }
 }
 
+// CFR+ linear averaging weights of iteration c.iter (CFRPlus.py:68-73)
+inline void set_avg_weights(Ctx2& c) {
+    const double cw = 0.5 * ((double)c.iter * (c.iter + 1) - (double)c.delay * (c.delay + 1));
+    const double nw = (double)c.iter - c.delay + 1;
+    c.m_old = (float)(cw / (cw + nw));
+    c.m_new = (float)(nw / (cw + nw));
+}
+
 inline unsigned blocks_for(long long threads) { return (unsigned)((threads + kThreads - 1) / kThreads); }
 
 int check_tree2(const prl_tree_t* t) {
@@ -477,6 +552,7 @@ int check_tree2(const prl_tree_t* t) {
         return prl::fail("prl(two-card): hand_cards / board tables missing");
     if (t->n_deck - 1 > 64 || t->n_deck - 1 >= kRowStride) return prl::fail("prl(two-card): deck too large for the card-row scans");
     if (t->n_sym > 1 && !t->sym_perm) return prl::fail("prl(two-card): sym_perm missing");
+    if (t->ld % 4 || t->ld < t->n_range) return prl::fail("prl(two-card): ld must be a multiple of 4 (float4 rows) and >= n_range");
     return 0;
 }
 
@@ -490,9 +566,9 @@ void reach_sweep2(Ctx2 c, bool update_avg, cudaStream_t s) {
         c.lo = (int)T.level_start[d];
         c.n = (int)(T.level_start[d + 1] - T.level_start[d]);
         if (c.n == 0) continue;
-        const unsigned g = blocks_for((long long)c.n * T.ld);
-        if (update_avg) reach2_kernel<true><<<g, kThreads, 0, s>>>(c);
-        else reach2_kernel<false><<<g, kThreads, 0, s>>>(c);
+        const dim3 g((unsigned)c.n, (unsigned)((T.n_range + 4 * kVecThreads - 1) / (4 * kVecThreads)));
+        if (update_avg) reach2_kernel<true><<<g, kVecThreads, 0, s>>>(c);
+        else reach2_kernel<false><<<g, kVecThreads, 0, s>>>(c);
         prl::count_launch();
     }
 }
@@ -525,10 +601,10 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
         if (n_dec > 0 && chance_phase != 2) {
             c.lo = lo;
             c.n = n_dec;
-            const unsigned g = blocks_for((long long)n_dec * T.ld);
-            if (update) value2_kernel<false, true><<<g, kThreads, 0, s>>>(c);
-            else if (with_br) value2_kernel<true, false><<<g, kThreads, 0, s>>>(c);
-            else value2_kernel<false, false><<<g, kThreads, 0, s>>>(c);
+            const dim3 g((unsigned)n_dec, (unsigned)((T.n_range + 4 * kVecThreads - 1) / (4 * kVecThreads)));
+            if (update) value2_kernel<false, true><<<g, kVecThreads, 0, s>>>(c);
+            else if (with_br) value2_kernel<true, false><<<g, kVecThreads, 0, s>>>(c);
+            else value2_kernel<false, false><<<g, kVecThreads, 0, s>>>(c);
             prl::count_launch();
         }
         if (n_chance > 0) {
@@ -566,7 +642,7 @@ namespace prl2 {
 
 int reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, const int* mode, cudaStream_t s) {
     if (int e = check_tree2(tree)) return e;
-    Ctx2 c{*tree, *buf, 0, 0, player_mask, {mode[0], mode[1]}, 0, -1, 0, 0};
+    Ctx2 c{*tree, *buf, 0, 0, player_mask, {mode[0], mode[1]}, 0, -1, 0, 0, 0.0f, 1.0f};
     reach_sweep2(c, false, s);
     return prl::check(cudaGetLastError(), "prl_reach_pass(two-card)");
 }
@@ -574,7 +650,7 @@ int reach_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask
 int value_pass(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int with_br, const int* mode,
                cudaStream_t s) {
     if (int e = check_tree2(tree)) return e;
-    Ctx2 c{*tree, *buf, 0, 0, player_mask, {mode[0], mode[1]}, 0, -1, 0, 0};
+    Ctx2 c{*tree, *buf, 0, 0, player_mask, {mode[0], mode[1]}, 0, -1, 0, 0, 0.0f, 1.0f};
     if (int e = value_sweep2(c, with_br != 0, false, s)) return e;
     return prl::check(cudaGetLastError(), "prl_value_pass(two-card)");
 }
@@ -588,7 +664,8 @@ int root_exploitability(const prl_tree_t* tree, const prl_buffers_t* buf, float*
 int cfr_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay, const int* mode,
               int which, cudaStream_t s) {
     if (int e = check_tree2(tree)) return e;
-    Ctx2 c{*tree, *buf, 0, 0, 1 << p, {mode[0], mode[1]}, algo, p, iter, delay};
+    Ctx2 c{*tree, *buf, 0, 0, 1 << p, {mode[0], mode[1]}, algo, p, iter, delay, 0.0f, 1.0f};
+    set_avg_weights(c);
     if (which & 1)
         if (int e = value_sweep2(c, false, true, s)) return e;
     if (which & 2) {
@@ -609,7 +686,7 @@ extern "C" int prl_value_levels(const prl_tree_t* tree, const prl_buffers_t* buf
     if (int e = check_tree2(tree)) return e;
     if (level_hi >= tree->n_levels || level_lo < 0 || level_hi < level_lo) return prl::fail("prl_value_levels: bad level range");
     if (with_br && algo >= 0) return prl::fail("prl_value_levels: the update sweep does not compute best responses");
-    Ctx2 c{*tree, *buf, 0, 0, player_mask, {strat_mode[0], strat_mode[1]}, algo < 0 ? 0 : algo, algo < 0 ? -1 : upd_p, iter, delay};
+    Ctx2 c{*tree, *buf, 0, 0, player_mask, {strat_mode[0], strat_mode[1]}, algo < 0 ? 0 : algo, algo < 0 ? -1 : upd_p, iter, delay, 0.0f, 1.0f};
     if (int e = value_levels2(c, with_br != 0, algo >= 0, level_hi, level_lo, chance_phase, (cudaStream_t)stream)) return e;
     return prl::check(cudaGetLastError(), "prl_value_levels");
 }

@@ -93,8 +93,17 @@ class BoardSpec:
         self.sym_perm = sym_perm
         self.note = note
 
+    _cache = {}
+
     @staticmethod
     def full_game(rules, isomorphic=True, deck_subset=None):
+        key = (rules.STRING, isomorphic, None if deck_subset is None else tuple(deck_subset))
+        if key not in BoardSpec._cache:
+            BoardSpec._cache[key] = BoardSpec._full_game(rules, isomorphic, deck_subset)
+        return BoardSpec._cache[key]
+
+    @staticmethod
+    def _full_game(rules, isomorphic=True, deck_subset=None):
         """All boards of the game's single deal (Flop5Holdem: five cards), as isomorphism classes by default.
         deck_subset: restrict the BOARD cards to these card ids (must be closed under suit permutations when
         isomorphic); hands still range over the whole deck.  The deal probability stays the full-game constant
