@@ -82,6 +82,23 @@ class CFRBase:
             self._log_curr_strat_expl()
             self._evaluate_avg_strats()
 
+    # ---- checkpoint / resume (extension; the reference's CFR classes implement none)
+    def state_dict(self):
+        return {"iter_counter": self._iter_counter, "solvers": [s.state_dict() for s in self._solvers]}
+
+    def load_state_dict(self, state):
+        self._iter_counter = state["iter_counter"]
+        for s, st in zip(self._solvers, state["solvers"]):
+            s.load_state_dict(st)
+
+    def checkpoint(self, path):
+        import torch
+        torch.save(self.state_dict(), path)
+
+    def load_checkpoint(self, path):
+        import torch
+        self.load_state_dict(torch.load(path, weights_only=False))
+
     def _metric(self, t_idx):
         return "Evaluation/" + self._env_bldrs[t_idx].env_cls.WIN_METRIC
 

@@ -256,6 +256,20 @@ class CFRSolver:
                 self.modes[p] = nat.STRAT_F32
             self.iter_counter += 1
 
+    # ---- checkpoint / resume (the reference's CFR classes keep regrets only inside node objects; WorkerBase.py:23-38 is
+    #      a no-op skeleton) - SURVEY.md §8f N1
+    def state_dict(self):
+        return {"algo": self.algo_name, "delay": self.delay, "iter_counter": self.iter_counter, "modes": list(self.modes),
+                "regret": self.bufs.regret.cpu(), "strat": self.bufs.strat.cpu(), "avg": self.bufs.avg.cpu()}
+
+    def load_state_dict(self, state):
+        assert state["algo"] == self.algo_name and state["regret"].shape == self.bufs.regret.shape
+        self.iter_counter, self.modes = int(state["iter_counter"]), list(state["modes"])
+        self.bufs.regret.copy_(state["regret"])
+        self.bufs.strat.copy_(state["strat"])
+        self.bufs.avg.copy_(state["avg"].to(self.bufs.avg.dtype))
+        self.ops.reach_pass(self.modes)  # reach rows are a function of the strategies
+
     # ---- evaluation (_CFRBase._log_curr_strat_expl :198-216, _evaluate_avg_strats :218-262)
     def _metric(self, expl):
         e = [float(expl[p]) * self.ev_normalizer for p in range(2)]

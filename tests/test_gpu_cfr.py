@@ -118,3 +118,51 @@ def test_persistent_multi_iteration_launch_matches_golden():
         s.iteration(20)
         assert s.exploitability_current() == g["curr_series"][t, 1]
         assert s.exploitability_average() == g["avg_series"][t - 1, 1]
+
+
+def test_local_br_master_with_tabular_agent_matches_internal_average_evaluation():
+    """LocalBRMaster(fill_with_agent_policy -> reach -> value+BR) on the tabular agent == the solver's own average-
+    strategy exploitability (LocalBRMaster.py:41-80 vs _CFRBase.py:218-262); also the pickle round trip."""
+    import os
+    import tempfile
+    from pokerrl_b200.cfr.CFRPlus import CFRPlus
+    from pokerrl_b200.cfr.TabularCFREvalAgent import TabularCFREvalAgent, average_strategy_table
+    from pokerrl_b200.eval.br.LocalBRMaster import LocalBRMaster
+    from pokerrl_b200.game import bet_sets
+    from pokerrl_b200.game.games import DiscretizedNLLeduc
+    from pokerrl_b200.rl.base_cls.TrainingProfileBase import TrainingProfileBase
+    from pokerrl_b200.rl.base_cls.workers.ChiefBase import ChiefBase
+    chief = ChiefBase(t_prof=None)
+    cfr = CFRPlus(name="k", chief_handle=chief, game_cls=DiscretizedNLLeduc, agent_bet_set=bet_sets.POT_ONLY, delay=0)
+    for _ in range(12):
+        cfr.iteration()
+    ref = chief.get_experiments()["k_Avg_total_S20000_CFRp_delay0"]["Evaluation/MBB_per_G"][-1][1]
+    t_prof = TrainingProfileBase("k", DiscretizedNLLeduc, bet_sets.POT_ONLY)
+    br = LocalBRMaster(t_prof=t_prof, chief_handle=chief, eval_agent_cls=TabularCFREvalAgent)
+    br.eval_agent.update_weights(average_strategy_table(cfr.solvers[0]))
+    br.evaluate(iter_nr=12)
+    got = chief.get_experiments()["k AVG_stack_20000: BR Total"]["Evaluation/MBB_per_G"][-1]
+    assert got[0] == 12 and got[1] == ref
+    with tempfile.TemporaryDirectory() as d:
+        br.eval_agent.store_to_disk(d, "agent")
+        again = TabularCFREvalAgent.load_from_disk(os.path.join(d, "agent.pkl"))
+        assert np.array_equal(again._table, br.eval_agent._table)
+
+
+def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
+    from pokerrl_b200.cfr.LinearCFR import LinearCFR
+    from pokerrl_b200.game import bet_sets
+    from pokerrl_b200.game.games import StandardLeduc
+    from pokerrl_b200.rl.base_cls.workers.ChiefBase import ChiefBase
+    g = golden("cfr_LinearCFR_StandardLeduc.npz")
+    a = LinearCFR(name="a", chief_handle=ChiefBase(None), game_cls=StandardLeduc, agent_bet_set=bet_sets.POT_ONLY, avg_f64=False)
+    for _ in range(5):
+        a.iteration()
+    a.checkpoint(str(tmp_path / "ck.pt"))
+    b = LinearCFR(name="b", chief_handle=ChiefBase(None), game_cls=StandardLeduc, agent_bet_set=bet_sets.POT_ONLY)
+    b.load_checkpoint(str(tmp_path / "ck.pt"))
+    for _ in range(5):
+        b.iteration()
+    assert b.iter_counter == 10
+    assert b.solvers[0].exploitability_current() == g["curr_series"][10, 1]
+    assert b.solvers[0].exploitability_average() == g["avg_series"][9, 1]
