@@ -208,6 +208,52 @@ void get_idx_2_hole_card_lut(int8_t** lut /*[1326][2]*/);
 int8_t get_1d_card(const int8_t* card_2d);
 void get_2d_card(int8_t card_1d, int8_t* out_card_2d);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Batched heads-up PokerEnv (replaces the scalar Python engine PokerRL/game/_/rl_env/base/PokerEnv.py for B tables at
+ * once).  One table per thread, integer chips, the reference's action decoding,
+ * legalisation, round logic, payouts, rewards and observation layout.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define PRL_ENV_MAX_ACTIONS 34
+
+typedef struct {
+    int32_t n_envs;
+    int32_t kind;          /* 0 = limit-type action space {fold, call, raise} (LimitPokerEnv.py), 1 = discretized pot
+                              fractions (DiscretizedPokerEnv.py) */
+    int32_t n_actions;     /* env_args.N_ACTIONS */
+    int32_t n_rounds;      /* len(ALL_ROUNDS_LIST) */
+    int32_t n_round_slots; /* ALL_ROUNDS_LIST[-1] + 1 (one-hot width in the observation) */
+    int32_t n_hole, n_ranks, n_suits, n_deck;
+    int32_t n_flop, n_turn, n_river;
+    int32_t small_blind, big_blind, ante, small_bet, big_bet, round_big_bet_starts;
+    int32_t max_raises[4]; /* MAX_N_RAISES_PER_ROUND */
+    int32_t first_action_no_call, limit_raise_is_pot, btn_first_postflop, suits_matter;
+    int32_t pair_bonus;    /* one-card games: hand strength bonus for pairing the board */
+    int32_t start_stack[2];
+    int32_t obs_size;      /* 7 + 3 + 2 + 2 + n_round_slots + 6 + n_board_cards * (n_ranks + n_suits) */
+    double fracs[32];      /* sorted bet sizes as fractions of the pot (kind 1) */
+    double reward_scalar;  /* REWARD_SCALAR (PokerEnv.py:361-368) */
+    double norm;           /* observation normaliser = mean starting stack (PokerEnv.py:1267) */
+} prl_env_cfg_t;
+
+/* number of int32 state fields per table; state = DEVICE int32[prl_env_state_fields()][n_envs] */
+int prl_env_state_fields(void);
+
+/* PokerEnv.reset (PokerEnv.py:1075-1122) for all tables.  deck = DEVICE int8[n_envs][n_deck], top card first: seat 0's
+ * hole cards, seat 1's, flop, turn, river (_Deck.py:23-27).  shuffle != 0 fills the decks from a counter RNG
+ * (seed, episode0 + table) instead of using the caller's.  obs = DEVICE float[n_envs][obs_size] or NULL,
+ * legal = DEVICE uint8[n_envs][n_actions] or NULL (get_legal_actions as a mask). */
+int prl_env_reset(const prl_env_cfg_t* cfg, int32_t* state, int8_t* deck, float* obs, uint8_t* legal, uint64_t seed,
+                  uint64_t episode0, int shuffle, prl_stream_t stream);
+
+/* PokerEnv.step (PokerEnv.py:1148-1159, 681-789) for all tables: actions = DEVICE int32[n_envs] discrete actions, or
+ * NULL / negative entries = uniformly random legal action from the counter RNG (seed, step_id).  Outputs (any may be
+ * NULL): obs (zeros at terminal states), rewards = DEVICE double[n_envs][2] ((stack - start) / REWARD_SCALAR at terminal
+ * steps, else 0), done = DEVICE uint8[n_envs], legal mask for the next step.  Finished tables ignore further steps unless
+ * auto_reset != 0, in which case they are re-dealt (counter RNG) and reset before the action is applied. */
+int prl_env_step(const prl_env_cfg_t* cfg, int32_t* state, int8_t* deck, const int32_t* actions, float* obs,
+                 double* rewards, uint8_t* done, uint8_t* legal, uint64_t seed, uint64_t step_id, int auto_reset,
+                 prl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

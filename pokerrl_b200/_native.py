@@ -38,6 +38,19 @@ class PrlBuffers(C.Structure):
                 ("workspace_bytes", C.c_uint64)]
 
 
+class PrlEnvCfg(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("kind", C.c_int32), ("n_actions", C.c_int32), ("n_rounds", C.c_int32),
+        ("n_round_slots", C.c_int32), ("n_hole", C.c_int32), ("n_ranks", C.c_int32), ("n_suits", C.c_int32),
+        ("n_deck", C.c_int32), ("n_flop", C.c_int32), ("n_turn", C.c_int32), ("n_river", C.c_int32),
+        ("small_blind", C.c_int32), ("big_blind", C.c_int32), ("ante", C.c_int32), ("small_bet", C.c_int32),
+        ("big_bet", C.c_int32), ("round_big_bet_starts", C.c_int32), ("max_raises", C.c_int32 * 4),
+        ("first_action_no_call", C.c_int32), ("limit_raise_is_pot", C.c_int32), ("btn_first_postflop", C.c_int32),
+        ("suits_matter", C.c_int32), ("pair_bonus", C.c_int32), ("start_stack", C.c_int32 * 2), ("obs_size", C.c_int32),
+        ("fracs", C.c_double * 32), ("reward_scalar", C.c_double), ("norm", C.c_double),
+    ]
+
+
 _lib = None
 
 
@@ -77,6 +90,13 @@ def lib():
     L.prl_hand_rank_7.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     for f in ("prl_hand_rank_boards", "prl_hand_rank_7"):
         getattr(L, f).restype = C.c_int
+    ep = C.POINTER(PrlEnvCfg)
+    L.prl_env_state_fields.restype = C.c_int
+    L.prl_env_reset.argtypes = [ep, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int,
+                                C.c_void_p]
+    L.prl_env_step.argtypes = [ep, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    L.prl_env_reset.restype = L.prl_env_step.restype = C.c_int
     _lib = L
     return L
 

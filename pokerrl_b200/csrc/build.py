@@ -22,6 +22,7 @@ SOURCES = {
     "cfr_levels.cu": ["-fmad=false"],
     "hand_eval.cu": [],
     "cfr_twocard.cu": [],
+    "env_kernels.cu": [],
 }
 
 
