@@ -35,7 +35,7 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 LEDUC = {"leduc_b5": "B_5", "leduc_b3": "B_3", "leduc_pot": "POT_ONLY"}
-WORKLOADS = ["fhp"] + list(LEDUC)
+WORKLOADS = ["fhp"] + list(LEDUC) + ["env", "handeval"]
 
 
 # ---------------------------------------------------------------------------------------------------------- workloads
@@ -166,6 +166,105 @@ def run_cpu_fhp(n_boards_sample, n_iters, n_boards_full):
     return sec * n_boards_full / nb, sec, nb, threads
 
 
+def run_aux(a):
+    """BASELINE.json configs[4]: 2^20 parallel heads-up DiscretizedNLHoldem tables (bet_sets.B_5, stacks 20000, uniformly
+    random legal actions from the counter RNG, finished hands re-dealt) and batched 7-card evaluation throughput."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    torch.cuda.set_device(0)
+    K = a.steps or 200
+    W = max(3, a.warmup or 5)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.workload == "env":
+        from pokerrl_b200.game import bet_sets, games
+        from pokerrl_b200.game.batched_env import BatchedPokerEnv
+        g = games.DiscretizedNLHoldem
+        args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=bet_sets.B_5)
+        B = 1 << 20
+        env = BatchedPokerEnv(g, args, B, seed=0)
+        env.reset()
+        for _ in range(W):
+            env.step(None, auto_reset=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(K):
+            env.step(None, auto_reset=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / K
+        # e2e: host-provided actions (pinned) in, rewards + done flags out, every step
+        acts = torch.zeros(B, dtype=torch.int32).pin_memory()
+        rew_h, done_h = torch.zeros(B, 2, dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory()
+        acts[:] = 1
+        t0 = time.perf_counter()
+        for _ in range(20):
+            _, r, d, _ = env.step(acts.to("cuda", non_blocking=True), auto_reset=True)
+            rew_h.copy_(r, non_blocking=True)
+            done_h.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e = 20 * B / (time.perf_counter() - t0)
+        bytes_per_step = B * (4 * 18 * 2 + 52 + env.obs_size * 4 + 16 + 1 + env.N_ACTIONS)
+        out = {"metric": "PokerEnv steps/s", "value": B / (ms * 1e-3), "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+               "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+               "data": "synthetic (counter-RNG decks and uniformly random legal actions)",
+               "config": {"workload": "2^20 heads-up DiscretizedNLHoldem tables, bet_sets.B_5 (7 actions), stacks 20000, eval "
+                                      "mode, random legal play with auto re-deal; obs float32[109] + rewards + done + legal mask "
+                                      "written every step"},
+               "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": B * 17},
+               "gpu_launches": K,
+               "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": bytes_per_step / (ms * 1e-3) / 1e9, "peak": peak,
+                            "unit": "GB/s", "frac": bytes_per_step / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                            "algorithmic_bytes_per_launch": bytes_per_step},
+               "cpu_baseline": {"value": 18300.0, "unit": "steps/s", "cores": 1, "kind": "reference",
+                                "sample": "not re-timed here: the reference env cannot travel to the GPU box; 18.3 k steps/s is "
+                                          "the reference's own PokerEnv random play measured in the build container (BASELINE.md)"}}
+    else:
+        from pokerrl_b200.hand_eval import hand_rank_all_hands_on_given_boards
+        rng = np.random.default_rng(0)
+        NB = 100000
+        boards = torch.from_numpy(np.stack([rng.permutation(52)[:5] for _ in range(NB)]).astype(np.int8)).cuda()
+        for _ in range(W):
+            out_t = hand_rank_all_hands_on_given_boards(boards)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(K):
+            out_t = hand_rank_all_hands_on_given_boards(boards)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / K
+        evals = NB * 1081
+        import cfr_c  # noqa: F401  (builds oracle/_build)
+        orc = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libhand_eval_oracle.so"))
+        orc.orc_rank_boards.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        hb = np.ascontiguousarray(boards[:4000].cpu().numpy())
+        ho = np.zeros((4000, 1326), np.int32)
+        t0 = time.perf_counter()
+        orc.orc_rank_boards(ho.ctypes.data, hb.ctypes.data, 4000)
+        cpu = 4000 * 1081 / (time.perf_counter() - t0)
+        assert np.array_equal(ho, out_t[:4000].cpu().numpy())
+        b = NB * (5 + 1326 * 4)
+        out = {"metric": "7-card hand evaluations/s", "value": evals / (ms * 1e-3), "unit": "evals/s", "n_gpus": 1, "steps": K,
+               "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+               "data": "synthetic (100 000 random boards, seed 0)",
+               "config": {"workload": "100 000 random 5-card boards x 1326 hands (1081 live each), int32 strengths identical to "
+                                      "lib_hand_eval.so"},
+               "e2e": {"value": None, "unit": "evals/s", "h2d_bytes_per_step": NB * 5, "d2h_bytes_per_step": NB * 1326 * 4},
+               "gpu_launches": K,
+               "roofline": {"bound": "hbm", "kernel": "rank_boards_kernel", "achieved": b / (ms * 1e-3) / 1e9, "peak": peak,
+                            "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": b},
+               "cpu_baseline": {"value": cpu, "unit": "evals/s", "cores": 1, "kind": "port",
+                                "sample": "4 000 boards x 1326 hands by oracle/hand_eval_oracle.c (output compared exactly); the "
+                                          "reference binary did 2.73 M evals/s on one core (BASELINE.md)"}}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +279,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.workload in ("env", "handeval"):
+        if rank == 0 and a.impl == "b200":
+            run_aux(a)
+        elif rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "aux workloads carry their CPU baseline in the main line"}))
+        return
     fhp = a.workload == "fhp"
     K = a.steps if a.steps is not None else (40 if fhp else 2000)
     W = max(3, a.warmup if a.warmup is not None else (3 if fhp else 20))
