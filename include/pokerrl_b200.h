@@ -92,6 +92,7 @@ typedef struct {
                                        strength order (-1 padded) */
     const uint8_t* board_row_pos;   /* DEVICE uint8[n_boards][n_range][4]: per hand {# weaker in row c1, # weaker in row
                                        c2, # weaker-or-equal in row c1, in row c2} */
+    const uint8_t* board_complete;  /* DEVICE uint8[n_boards]: 1 iff the board shows all N_TOTAL_BOARD_CARDS (tables above valid) */
     int32_t n_sym;               /* hand permutations summed at chance parents (24 suit permutations with isomorphism, else 0/1) */
     const int16_t* sym_perm;     /* DEVICE int16[n_sym][n_range] */
     float eq_const;              /* opponent-hand normaliser C(deck,2)/C(deck-2,2) (ValueFiller.py:19 generalised) */

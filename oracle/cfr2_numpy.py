@@ -69,6 +69,8 @@ class Oracle2Tree:
     def update_reach(self):
         ft = self.ft
         self.reach[0] = 1.0 / self.R
+        if ft.board[0] >= 0:  # sub-game root that already shows a board: blocked hands cannot be held
+            self.reach[0][:, self.board_blocked[ft.board[0]]] = 0.0
         for n in range(self.N):
             nc = ft.n_children[n]
             if nc == 0:

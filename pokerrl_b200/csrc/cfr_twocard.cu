@@ -98,8 +98,11 @@ __global__ void __launch_bounds__(kVecThreads) reach2_kernel(const Ctx2 c) {
         if (!(c.mask & (1 << q))) continue;
         float* reach_q = c.B.reach + (size_t)q * N * ld;
         F4 r;
-        if (par < 0) {
-            r = splat(1.0f / (float)R);  // PublicTree.py:122-124
+        if (par < 0) {  // PublicTree.py:122-124; a sub-game root that already shows a board zeroes the blocked hands
+            const int b = c.T.board[n];
+            const unsigned long long bm = (b >= 0) ? c.T.board_mask[b] : 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r.v[i] = (h0 + i < R && !hand_blocked(c.T, h0 + i, bm)) ? 1.0f / (float)R : 0.0f;
         } else {
             const F4 rp = ld4(reach_q + (size_t)par * ld + h0);
             const int pk = c.T.kind[par];
@@ -341,11 +344,12 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
     const float K = c.T.eq_const;
     const float half_pot = c.T.pot[n];
     const unsigned long long bmask = (b >= 0) ? c.T.board_mask[b] : 0ull;
-    const int16_t* gs_tab = (b >= 0 && c.T.board_gs) ? c.T.board_gs + (size_t)b * R : nullptr;
-    const int16_t* ge_tab = (b >= 0 && c.T.board_ge) ? c.T.board_ge + (size_t)b * R : nullptr;
-    const int16_t* pos_tab = (b >= 0 && c.T.board_pos) ? c.T.board_pos + (size_t)b * R : nullptr;
-    const int16_t* row_order = (b >= 0) ? c.T.board_row_order + (size_t)b * n_deck * (n_deck - 1) : nullptr;
-    const uchar4* row_pos = (b >= 0) ? reinterpret_cast<const uchar4*>(c.T.board_row_pos) + (size_t)b * R : nullptr;
+    const bool complete = b >= 0 && c.T.board_complete[b];  // strength tables exist for complete boards only
+    const int16_t* gs_tab = complete ? c.T.board_gs + (size_t)b * R : nullptr;
+    const int16_t* ge_tab = complete ? c.T.board_ge + (size_t)b * R : nullptr;
+    const int16_t* pos_tab = complete ? c.T.board_pos + (size_t)b * R : nullptr;
+    const int16_t* row_order = complete ? c.T.board_row_order + (size_t)b * n_deck * (n_deck - 1) : nullptr;
+    const uchar4* row_pos = complete ? reinterpret_cast<const uchar4*>(c.T.board_row_pos) + (size_t)b * R : nullptr;
 #pragma unroll 1
     for (int p = 0; p < 2; ++p) {
         if (!(c.mask & (1 << p))) continue;
@@ -550,7 +554,8 @@ inline unsigned blocks_for(long long threads) { return (unsigned)((threads + kTh
 int check_tree2(const prl_tree_t* t) {
     if (!t || !t->level_start || !t->order || !t->level_nonterm || !t->level_ndec)
         return prl::fail("prl(two-card): level_start / order / level_nonterm / level_ndec missing");
-    if (!t->hand_cards || !t->board_mask || !t->board_prob || !t->board_mult || !t->board_row_order || !t->board_row_pos)
+    if (!t->hand_cards || !t->board_mask || !t->board_prob || !t->board_mult || !t->board_row_order || !t->board_row_pos ||
+        !t->board_complete)
         return prl::fail("prl(two-card): hand_cards / board tables missing");
     if (t->n_deck - 1 > 64 || t->n_deck - 1 >= kRowStride) return prl::fail("prl(two-card): deck too large for the card-row scans");
     if (t->n_sym > 1 && !t->sym_perm) return prl::fail("prl(two-card): sym_perm missing");

@@ -21,7 +21,26 @@ from pokerrl_b200.solver import CFRSolver, TreeBuffers, TreeOps, _stream
 
 
 def shard_board_spec(spec, rank, world):
-    """boards rank, rank + world, ... of `spec` (every board subtree has the same cost, so round-robin balances)"""
+    """boards rank, rank + world, ... of the FIRST chance layer of `spec` (every board subtree has the same cost, so
+    round-robin balances); deeper layers follow their parents"""
+    from pokerrl_b200.game.holdem_boards import MultiStreetBoards
+    if isinstance(spec, MultiStreetBoards):
+        boards, parents, prob, mult = [spec.boards[0]], [spec.parents[0]], [spec.prob[0]], [spec.mult[0]]
+        keep = np.arange(rank, spec.boards[1].shape[0], world)
+        new_parent = np.zeros(keep.size, np.int32)
+        for c in range(1, spec.n_layers + 1):
+            if c > 1:
+                old = spec.parents[c]
+                remap = np.full(spec.boards[c - 1].shape[0], -1, np.int64)
+                remap[prev_keep] = np.arange(prev_keep.size)
+                keep = np.nonzero(remap[old] >= 0)[0]
+                new_parent = remap[old[keep]].astype(np.int32)
+            boards.append(spec.boards[c][keep])
+            parents.append(new_parent)
+            prob.append(spec.prob[c][keep])
+            mult.append(spec.mult[c][keep])
+            prev_keep = keep
+        return MultiStreetBoards(boards, parents, prob, mult, "%s; shard %d/%d" % (spec.note, rank, world))
     sel = np.arange(rank, spec.boards.shape[0], world)
     return BoardSpec(spec.boards[sel], spec.board_prob[sel], spec.board_mult[sel], spec.sym_perm,
                      "%s; shard %d/%d (%d boards)" % (spec.note, rank, world, sel.size))
@@ -32,25 +51,38 @@ class ShardedCFRSolver(CFRSolver):
     world == 1 (or no process group) runs the same split schedule without communication."""
 
     def __init__(self, game_cls, env_args, board_spec, algo="CFRPlus", delay=0, device=None, rank=0, world=1,
-                 group=None):
+                 group=None, root_actions=None):
         self.rank, self.world, self.group = rank, world, group
-        ft = FlatTree(game_cls, env_args, board_spec=shard_board_spec(board_spec, rank, world) if world > 1 else board_spec)
+        ft = FlatTree(game_cls, env_args, board_spec=shard_board_spec(board_spec, rank, world) if world > 1 else board_spec,
+                      root_actions=root_actions)
         self.ft = ft
         super().__init__(ft, algo=algo, delay=delay, device=device, avg_f64=False, persistent=False)
-        self._chance_levels = [d for d in range(ft.n_levels)
-                               if np.any(ft.kind[int(ft.level_start[d]):int(ft.level_start[d + 1])] == nat.KIND_CHANCE)]
+        # levels holding BOUNDARY chance nodes: chance nodes right below the replicated trunk (no deal above them), whose
+        # children - the boards of the first chance layer - are spread over the ranks.  Deeper chance nodes are local.
+        self._n_chance, self._n_boundary = {}, {}
+        for d in range(ft.n_levels):
+            lo, hi = int(ft.level_start[d]), int(ft.level_start[d + 1])
+            ch = ft.kind[lo:hi] == nat.KIND_CHANCE
+            if ch.any():
+                self._n_chance[d] = int(ch.sum())
+                self._n_boundary[d] = int((ch & (ft.cdepth[lo:hi] == 0)).sum())
+        self._chance_levels = [d for d in self._n_chance if self._n_boundary[d] > 0]
         self.n_allreduce = 0
 
     # ---- the one collective of the path
-    def _allreduce_chance_sums(self, bufs, level):
-        ft, dt = self.ft, self.dtree
-        n_chance = int((ft.kind[int(ft.level_start[level]):int(ft.level_start[level + 1])] == nat.KIND_CHANCE).sum())
+    def _allreduce_chance_sums(self, bufs, level, arrays):
+        """all-reduce the per-node sums W of the boundary chance nodes of `level` (they come first in the work list);
+        W is laid out [4][n_chance][ld] at float offset 4 * n_chance * chunks * ld of the workspace"""
+        dt = self.dtree
+        n_chance, n_b = self._n_chance[level], self._n_boundary[level]
         chunks = -(-dt.desc.max_chance_children // 128)
         w_off = 4 * n_chance * chunks * dt.ld
-        view = bufs.workspace[w_off:w_off + 4 * n_chance * dt.ld]
-        if self.world > 1:
-            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
-        self.n_allreduce += 1
+        for arr in arrays:
+            o = w_off + arr * n_chance * dt.ld
+            view = bufs.workspace[o:o + n_b * dt.ld]
+            if self.world > 1:
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            self.n_allreduce += 1
 
     def _value_sweep(self, bufs, mask, with_br, algo, upd_p, modes):
         tree, buf = C.byref(self.dtree.desc), C.byref(bufs.desc)
@@ -59,12 +91,13 @@ class ShardedCFRSolver(CFRSolver):
             nat.call("prl_value_levels", tree, buf, mask, int(with_br), algo, upd_p, self.iter_counter, self.delay,
                      nat.modes(*modes), hi, lo, phase, _stream())
 
+        arrays = [2 * p + k for p in (0, 1) if mask & (1 << p) for k in ((0, 1) if with_br else (0,))]
         hi = self.ft.n_levels - 1
         for d in sorted(self._chance_levels, reverse=True):
             if hi > d:
                 levels(hi, d + 1, 0)
             levels(d, d, 1)
-            self._allreduce_chance_sums(bufs, d)
+            self._allreduce_chance_sums(bufs, d, arrays)
             levels(d, d, 2)
             hi = d - 1
         if hi >= 0:

@@ -108,32 +108,51 @@ def make_board_tables(rules, n_cdepth, root_board=()):
 class FlatTree:
     """Depth-sorted structure-of-arrays public tree (host numpy; uploaded to HBM by the solver)."""
 
-    def __init__(self, game_cls, env_args, stop_at_street=None, board_tables=None, board_spec=None):
-        """board_spec (two-card games): a `holdem_boards.BoardSpec` naming the boards dealt at the single chance layer,
-        their deal probability, their weight in the parent's sum and the suit-permutation tables; default = all boards
-        of the game as suit-isomorphism classes."""
+    def __init__(self, game_cls, env_args, stop_at_street=None, board_tables=None, board_spec=None, root_actions=None):
+        """board_spec (two-card games): a `holdem_boards.BoardSpec` (one chance layer: the boards dealt, their deal
+        probability, their weight in the parent's sum, suit-permutation tables; default = all boards of the game as
+        suit-isomorphism classes) or a `holdem_boards.MultiStreetBoards` (sub-game rooted at a fixed board with
+        several chance layers).  root_actions: discrete actions played from the start of the hand to reach the root of a
+        sub-game (the reference roots a tree at "the current state of the environment", PublicTree.py:37-40, 111-126)."""
         self.game_cls = game_cls
         self.rules = game_cls.RULES
         self.R = self.rules.RANGE_SIZE
         self.betting = eng.HUBetting(game_cls, env_args)
-        self.abs_nodes = enumerate_betting_tree(self.betting, stop_at_street=stop_at_street)
+        root_state = None
+        if root_actions:
+            root_state = self.betting.reset()
+            for a in root_actions:
+                out, _ = self.betting.step(root_state, a)
+                assert out in (eng.CONTINUE, eng.NEXT_ROUND), "root_actions must not end the hand"
+        self.root_round = 0 if root_state is None else root_state.round
+        self.abs_nodes = enumerate_betting_tree(self.betting, root_state=root_state, stop_at_street=stop_at_street)
         self.board_spec = None
+        self.root_has_board = False
         if self.rules.N_HOLE_CARDS == 2:
-            from pokerrl_b200.game.holdem_boards import BoardSpec
+            from pokerrl_b200.game.holdem_boards import BoardSpec, MultiStreetBoards
             n_cd = max(n.cdepth for n in self.abs_nodes)
-            if n_cd > 1:
-                raise NotImplementedError("two-card games with more than one chance layer (turn/river deals)")
             if any(n.kind == KIND_SHOWDOWN_ALLIN for n in self.abs_nodes):
                 raise NotImplementedError("all-in showdowns before the board is complete in two-card games")
             if board_spec is None:
+                if n_cd > 1 or root_state is not None:
+                    raise ValueError("sub-games / multi-street two-card trees need an explicit MultiStreetBoards spec")
                 board_spec = BoardSpec.full_game(self.rules)
             self.board_spec = board_spec
-            board_tables = ([np.zeros((1, 0), np.int8), board_spec.boards],
-                            [np.zeros(1, np.int32), np.zeros(board_spec.boards.shape[0], np.int32)])
+            if isinstance(board_spec, MultiStreetBoards):
+                assert board_spec.n_layers == n_cd, (board_spec.n_layers, n_cd)
+                board_tables = (board_spec.boards, board_spec.parents)
+                self.root_has_board = board_spec.boards[0].shape[1] > 0
+                self.board_prob = np.concatenate(board_spec.prob).astype(np.float32)
+                self.board_mult = np.concatenate(board_spec.mult).astype(np.float32)
+            else:
+                if n_cd != 1:
+                    raise ValueError("a BoardSpec describes exactly one chance layer")
+                board_tables = ([np.zeros((1, 0), np.int8), board_spec.boards],
+                                [np.zeros(1, np.int32), np.zeros(board_spec.boards.shape[0], np.int32)])
+                # per global board id (0 = the empty pre-deal board)
+                self.board_prob = np.concatenate([[1.0], board_spec.board_prob]).astype(np.float32)
+                self.board_mult = np.concatenate([[1.0], board_spec.board_mult]).astype(np.float32)
         self._expand(board_tables)
-        if self.board_spec is not None:  # per global board id (0 = the empty pre-deal board)
-            self.board_prob = np.concatenate([[1.0], self.board_spec.board_prob]).astype(np.float32)
-            self.board_mult = np.concatenate([[1.0], self.board_spec.board_mult]).astype(np.float32)
 
     # ------------------------------------------------------------------
     def _expand(self, board_tables):
@@ -211,6 +230,7 @@ class FlatTree:
         rnd = np.zeros(N, np.int8)
         board = np.full(N, -1, np.int32)
         abs_id = np.zeros(N, np.int32)
+        cdepth = np.zeros(N, np.int8)
         stack = np.zeros((N, 2), np.int64)
         bet = np.zeros((N, 2), np.int64)
         dfs_rel = np.zeros(N, np.int64)
@@ -236,9 +256,11 @@ class FlatTree:
             pot[flat] = rep(a_pot)
             rnd[flat] = rep(a_round)
             abs_id[flat] = np.repeat(sel.astype(np.int32), nb[c])
+            cdepth[flat] = c
             stack[flat] = np.repeat(a_stack[sel], nb[c], axis=0)
             bet[flat] = np.repeat(a_bet[sel], nb[c], axis=0)
-            board[flat] = np.tile(board_off[c] + np.arange(nb[c]), sel.size) if c > 0 else -1
+            board[flat] = (np.tile(board_off[c] + np.arange(nb[c]), sel.size)
+                           if (c > 0 or getattr(self, "root_has_board", False)) else -1)
             # parents
             par_abs = a_parent[sel]
             has_par = par_abs >= 0
@@ -282,6 +304,7 @@ class FlatTree:
         self.parent, self.first_child, self.n_children = parent, first_child, n_children
         self.kind, self.acted_last, self.action = kind, acted_last, action
         self.pot, self.round, self.board, self.abs_id = pot, rnd, board, abs_id
+        self.cdepth = cdepth  # number of chance deals above the node
         self.stack, self.bet = stack, bet
         self.dfs = dfs
         self.slot, self.first_slot = slot, first_slot
@@ -315,7 +338,10 @@ class FlatTree:
         a warp of the GPU sweeps holds nodes of one kind; level_nonterm[d] = number of non-terminals of level d."""
         order = np.empty(self.n_nodes, np.int32)
         level_nonterm = np.zeros(self.n_levels, np.int64)
-        key = self.kind.astype(np.int64) * (1 << 32) + self.n_children.astype(np.int64)
+        # (kind, chance depth, fan-out): among the chance nodes of a level those closest to the root come first - they
+        # are the ones whose children are sharded over GPUs (pokerrl_b200/distributed.py)
+        key = (self.kind.astype(np.int64) * (1 << 40) + self.cdepth.astype(np.int64) * (1 << 32)
+               + self.n_children.astype(np.int64))
         for d in range(self.n_levels):
             lo, hi = int(self.level_start[d]), int(self.level_start[d + 1])
             order[lo:hi] = lo + np.argsort(key[lo:hi], kind="stable")

@@ -123,3 +123,43 @@ class BoardSpec:
         perms = suit_permutation_hand_tables(rules.N_RANKS, rules.N_SUITS)
         return BoardSpec(reps, np.full(reps.shape[0], prob), orbit / float(perms.shape[0]), perms,
                          "%d suit-isomorphism classes of %d boards" % (reps.shape[0], boards.shape[0]))
+
+
+class MultiStreetBoards:
+    """Boards of a sub-game rooted at a fixed public board with one chance layer per remaining street (e.g. a Hold'em
+    flop: layer 1 = turn cards, layer 2 = river cards).  boards[c] = int8 [nb_c, n_cards_out] (children of one parent
+    contiguous, ascending card order like PublicTree.py:193-203), parents[c] = int32 [nb_c], prob[c] / mult[c] per
+    board.  Deal probability of a k-card deal with m cards already out: 1 / C(n_deck - m - 2 * n_hole, k) - the
+    generalisation of the reference's 1 / (N_CARDS_IN_DECK - 2) (StrategyFiller.py:159-166)."""
+
+    def __init__(self, boards, parents, prob, mult, note=""):
+        self.boards, self.parents, self.prob, self.mult, self.note = boards, parents, prob, mult, note
+        self.n_layers = len(boards) - 1
+        self.sym_perm = None
+
+    @staticmethod
+    def subgame(rules, root_board, n_layers, root_round, cards_per_layer=None):
+        """every card not on the board at each of the next n_layers deals (cards_per_layer: optional restriction of the
+        candidate cards of each layer, for small test trees; probabilities stay the full-game constants)"""
+        n_deck, n_hole = rules.N_CARDS_IN_DECK, rules.N_HOLE_CARDS
+        boards = [np.array([sorted(root_board)], dtype=np.int8).reshape(1, len(root_board))]
+        parents, prob, mult = [np.zeros(1, np.int32)], [np.ones(1)], [np.ones(1)]
+        rnd = root_round
+        for layer in range(1, n_layers + 1):
+            rnd += 1
+            k = rules.n_cards_dealt_in_transition_to(rnd)
+            prev = boards[-1]
+            rows, par = [], []
+            allowed = None if cards_per_layer is None else set(cards_per_layer[layer - 1])
+            for j in range(prev.shape[0]):
+                used = set(prev[j].tolist())
+                free = [x for x in range(n_deck) if x not in used and (allowed is None or x in allowed)]
+                for combo in combinations(free, k):
+                    rows.append(list(prev[j]) + list(combo))
+                    par.append(j)
+            boards.append(np.array(rows, dtype=np.int8).reshape(len(rows), prev.shape[1] + k))
+            parents.append(np.array(par, dtype=np.int32))
+            prob.append(np.full(len(rows), 1.0 / comb(n_deck - prev.shape[1] - 2 * n_hole, k)))
+            mult.append(np.ones(len(rows)))
+        return MultiStreetBoards(boards, parents, prob, mult,
+                                 "sub-game at board %s, %s boards per layer" % (list(root_board), [b.shape[0] for b in boards]))

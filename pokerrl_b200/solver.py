@@ -103,7 +103,9 @@ class DeviceTree:
         self.t_board_mask = torch.from_numpy(mask.view(np.int64)).to(dev)
         self.t_board_prob = up(ft.board_prob, np.float32)
         self.t_board_mult = up(ft.board_mult, np.float32)
-        complete = np.nonzero((bc >= 0).sum(axis=1) == 5)[0]
+        is_complete = (bc >= 0).sum(axis=1) == rules.N_TOTAL_BOARD_CARDS
+        self.t_board_complete = up(is_complete, np.uint8)
+        complete = np.nonzero(is_complete)[0]
         gs = torch.full((nb, self.R), -1, dtype=torch.int16, device=dev)
         ge, pos = torch.full_like(gs, -1), torch.full_like(gs, -1)
         n_deck = rules.N_CARDS_IN_DECK
@@ -138,6 +140,7 @@ class DeviceTree:
         d.board_mult = self.t_board_mult.data_ptr()
         d.board_gs, d.board_ge, d.board_pos = gs.data_ptr(), ge.data_ptr(), pos.data_ptr()
         d.board_row_order, d.board_row_pos = row_order.data_ptr(), row_pos.data_ptr()
+        d.board_complete = self.t_board_complete.data_ptr()
         d.n_sym = 0 if sp is None else int(sp.shape[0])
         d.sym_perm = self.t_sym_perm.data_ptr() if sp is not None else None
         n_deck, n_hole = rules.N_CARDS_IN_DECK, rules.N_HOLE_CARDS

@@ -11,13 +11,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_rank_sharded_fhp_matches_single_gpu():
+@pytest.mark.parametrize("which", ["fhp", "hulh"])
+def test_two_rank_sharded_matches_single_gpu(which):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29517",
-                          os.path.join(ROOT, "tools", "sharded_check.py")], capture_output=True, text=True, timeout=600)
+                          os.path.join(ROOT, "tools", "sharded_check.py"), which], capture_output=True, text=True,
+                         timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     r = json.loads(line)

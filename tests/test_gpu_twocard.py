@@ -107,3 +107,29 @@ def test_sharded_schedule_single_rank_equals_plain_solver():
 def torch_equal(x, y):
     import torch
     return bool(torch.equal(x, y))
+
+
+def test_multi_street_subgame_matches_oracle():
+    """Limit Hold'em sub-game rooted at a flop (two chance layers: turn and river, cards restricted to keep the oracle
+    fast): values under the uniform profile and three Linear CFR iterations (BASELINE.json configs[3] structure)."""
+    from pokerrl_b200.solver import CFRSolver
+    from twocard_common import hulh_flop_subgame
+    ft = hulh_flop_subgame([[20, 21, 22], [30, 31]])
+    orc = oracle_tree(ft)
+    orc.fill_uniform()
+    expl = orc.compute_ev()
+    s = CFRSolver(ft, "LinearCFR")
+    m = s.exploitability_current()
+    _close("reach", _node_vec(s.bufs.reach, ft), orc.reach)
+    _close("ev", _node_vec(s.bufs.ev, ft), orc.ev)
+    _close("ev_br", _node_vec(s.bufs.ev_br, ft), orc.ev_br)
+    ref_m = float(sum(expl) / 2 * ft.game_cls.EV_NORMALIZER)
+    assert abs(m - ref_m) <= 1e-5 * abs(ref_m)
+    c = o2.Oracle2CFR(orc, "LinearCFR", ev_normalizer=ft.game_cls.EV_NORMALIZER)
+    for t in range(3):
+        s.iteration(1)
+        c.iteration()
+        a, b = s.exploitability_current(), c.exploitability_current()
+        assert abs(a - b) <= 5e-5 * abs(b), (t, a, b)
+        a, b = s.exploitability_average(), c.exploitability_average()
+        assert abs(a - b) <= 5e-5 * abs(b), (t, a, b)

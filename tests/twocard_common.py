@@ -33,8 +33,21 @@ def oracle_tree(ft):
     """float64 oracle over the same flat tree / board spec"""
     spec = ft.board_spec
     lut = ft.rules.get_lut_holder()
-    ranks = np.concatenate([np.full((1, ft.R), -1, np.int32), oracle_ranks(spec.boards)])
+    bc = ft.board_cards()  # every board of every chance depth, global board id order
+    ranks = np.full((bc.shape[0], ft.R), -1, np.int32)
+    complete = np.nonzero((bc >= 0).sum(axis=1) == 5)[0]
+    if complete.size:
+        ranks[complete] = oracle_ranks(bc[complete])
     return o2.Oracle2Tree(ft, lut.LUT_IDX_2_HOLE_CARDS, ranks, ft.board_prob, ft.board_mult, spec.sym_perm)
+
+
+def hulh_flop_subgame(cards_per_layer, root_board=(0, 5, 10), stack=48):
+    """LimitHoldem sub-game rooted at a flop after SB limps / BB checks; turn and river cards restricted for tests"""
+    from pokerrl_b200.game.holdem_boards import MultiStreetBoards
+    g = games.LimitHoldem
+    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[stack, stack], bet_sizes_list_as_frac_of_pot=[1.0])
+    spec = MultiStreetBoards.subgame(g.RULES, root_board, 2, 1, cards_per_layer=cards_per_layer)
+    return FlatTree(g, args, board_spec=spec, root_actions=[1, 1])
 
 
 def random_board_spec(n, seed):
