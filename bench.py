@@ -35,7 +35,8 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 LEDUC = {"leduc_b5": "B_5", "leduc_b3": "B_3", "leduc_pot": "POT_ONLY"}
-WORKLOADS = ["fhp"] + list(LEDUC) + ["env", "handeval"]
+WORKLOADS = ["fhp", "hulh"] + list(LEDUC) + ["env", "handeval"]
+HULH_FLOP = (0, 5, 10)  # 2h 3d 4s
 
 
 # ---------------------------------------------------------------------------------------------------------- workloads
@@ -274,6 +275,7 @@ def main():
     ap.add_argument("--workload", default="fhp", choices=WORKLOADS)
     ap.add_argument("--eval-every", type=int, default=20)
     ap.add_argument("--fhp-boards", type=int, default=0, help="debug: only the first n isomorphism classes")
+    ap.add_argument("--hulh-turns", type=int, default=0, help="hulh: only the first n turn cards (memory: the full 49 need >= 2 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -285,11 +287,18 @@ def main():
         elif rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": "aux workloads carry their CPU baseline in the main line"}))
         return
-    fhp = a.workload == "fhp"
+    hulh = a.workload == "hulh"
+    fhp = a.workload in ("fhp", "hulh")  # two-card workloads share the sharded engine and the sweep-level roofline
+    algo_name = "LinearCFR" if hulh else "CFRPlus"
     K = a.steps if a.steps is not None else (40 if fhp else 2000)
     W = max(3, a.warmup if a.warmup is not None else (3 if fhp else 20))
     N_CLASSES = 134459
-    if fhp:
+    if hulh:
+        cfg = {"workload": "LimitHoldem (blinds 1/2, bets 2/4, 4 raises per round, stack 48) Linear CFR on the public sub-game "
+                           "rooted at the flop 2h3d4s after SB limps / BB checks: turn (49 cards) and river (48 cards) chance "
+                           "layers, 190 954 round-subtrees, range 1326, exact BR (current+average) every %d iterations%s"
+                           % (a.eval_every, " [DEBUG: first %d turn cards]" % a.hulh_turns if a.hulh_turns else "")}
+    elif fhp:
         cfg = {"workload": "Flop5Holdem CFR+ delay 0, full game: 134 459 suit-isomorphism classes of the 2 598 960 "
                            "five-card boards, range 1326, stack 20000, exact BR (current+average) every %d iterations"
                            % a.eval_every}
@@ -303,6 +312,10 @@ def main():
         if rank != 0:
             return
         ncpu = os.cpu_count() or 1
+        if hulh:
+            print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the hulh sub-game workload (the float64 oracle is "
+                              "exercised on a restricted sub-game in tests/test_gpu_twocard.py)"}))
+            return
         if fhp:
             K = min(K, 10)
             full_sec, sec, nb, threads = run_cpu_fhp(32, K, N_CLASSES)
@@ -343,15 +356,26 @@ def main():
     if fhp:
         from pokerrl_b200.distributed import ShardedCFRSolver
         from pokerrl_b200.game.holdem_boards import BoardSpec
-        g, args = fhp_args()
-        spec = BoardSpec.full_game(g.RULES)
-        if a.fhp_boards:
+        root_actions = None
+        if hulh:
+            from pokerrl_b200.game import games
+            from pokerrl_b200.game.holdem_boards import MultiStreetBoards
+            g = games.LimitHoldem
+            args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[48, 48], bet_sizes_list_as_frac_of_pot=[1.0])
+            free = [c for c in range(52) if c not in HULH_FLOP]
+            cpl = [free[:a.hulh_turns], free] if a.hulh_turns else None
+            spec = MultiStreetBoards.subgame(g.RULES, HULH_FLOP, 2, 1, cards_per_layer=cpl)
+            root_actions = [1, 1]
+        else:
+            g, args = fhp_args()
+            spec = BoardSpec.full_game(g.RULES)
+        if a.fhp_boards and not hulh:
             spec = BoardSpec(spec.boards[:a.fhp_boards], spec.board_prob[:a.fhp_boards], spec.board_mult[:a.fhp_boards],
                              spec.sym_perm, "first %d classes (debug)" % a.fhp_boards)
             cfg["workload"] += " [DEBUG SUBSET: %d classes]" % a.fhp_boards
         t_build = time.perf_counter() - t0
         t0 = time.perf_counter()
-        s = ShardedCFRSolver(g, args, spec, "CFRPlus", device=dev, rank=rank, world=world)
+        s = ShardedCFRSolver(g, args, spec, algo_name, device=dev, rank=rank, world=world, root_actions=root_actions)
         ft = s.ft
     else:
         g, ft = make_tree(a.workload, 20000 + 1000 * rank)
@@ -472,13 +496,31 @@ def main():
     torch.cuda.empty_cache()
     chief = ChiefBase(t_prof=None)
     with contextlib.redirect_stdout(io.StringIO()):
-        if fhp:
+        if hulh:
+            cfr = None  # the facade constructs full games; the sub-game is driven through the engine API (same calls)
+        elif fhp:
             cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=games.Flop5Holdem, agent_bet_set=[1.0], delay=0,
                           eval_every=a.eval_every, device=dev, board_spec=spec)
         else:
             cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=games.DiscretizedNLLeduc,
                           agent_bet_set=list(getattr(bet_sets, LEDUC[a.workload])),
                           starting_stack_sizes=[20000 + 1000 * rank], delay=0, eval_every=a.eval_every, device=dev)
+    if cfr is None:
+        s = ShardedCFRSolver(g, args, spec, algo_name, device=dev, rank=rank, world=world, root_actions=root_actions)
+
+        class _Engine:  # iteration + host read-back of the exploitability numbers at the evaluation cadence
+            n = 0
+
+            def iteration(self):
+                s.iteration(1)
+                self.n += 1
+                if self.n % a.eval_every == 0:
+                    return s.exploitability_current(), s.exploitability_average()
+
+            def reset(self):
+                s.reset()
+                self.n = 0
+        cfr = _Engine()
     for _ in range(W):
         cfr.iteration()
     cfr.reset()
@@ -502,7 +544,7 @@ def main():
         return
     jobs = 1 if fhp else world  # fhp: ONE game sharded over the ranks; Leduc: one tree per rank
     out = {
-        "metric": "CFR+ iterations/s", "value": jobs * K / (max_ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
+        "metric": ("Linear CFR" if hulh else "CFR+") + " iterations/s", "value": jobs * K / (max_ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True,
         "scaling": "strong" if fhp else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (deterministic game tree, no dataset)",
@@ -525,7 +567,9 @@ def main():
     }
     if world == 1 and not a.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
-        if fhp:
+        if hulh:
+            pass
+        elif fhp:
             full_sec, sec, nb, threads = run_cpu_fhp(32, 10, N_CLASSES)
             out["cpu_baseline"] = {"value": 1.0 / full_sec, "unit": "iterations/s", "cores": threads, "kind": "port",
                                    "sample": "10 CFR+ iterations of oracle/cfr2_numpy.py (float64 numpy) on %d random "
