@@ -51,7 +51,7 @@ class ShardedCFRSolver(CFRSolver):
     world == 1 (or no process group) runs the same split schedule without communication."""
 
     def __init__(self, game_cls, env_args, board_spec, algo="CFRPlus", delay=0, device=None, rank=0, world=1,
-                 group=None, root_actions=None):
+                 group=None, root_actions=None, fused=False):
         self.rank, self.world, self.group = rank, world, group
         ft = FlatTree(game_cls, env_args, board_spec=shard_board_spec(board_spec, rank, world) if world > 1 else board_spec,
                       root_actions=root_actions)
@@ -68,6 +68,25 @@ class ShardedCFRSolver(CFRSolver):
                 self._n_boundary[d] = int((ch & (ft.cdepth[lo:hi] == 0)).sum())
         self._chance_levels = [d for d in self._n_chance if self._n_boundary[d] > 0]
         self.n_allreduce = 0
+        # CFR+ on a tree with ONE chance layer and a small post-deal subtree (Flop5Holdem): optional fused per-board sweeps
+        # (board subtree in shared memory; correct but, in round 1, ~15 % SLOWER than the level sweeps - DESIGN.md §9 -
+        # hence off by default)
+        self._sub = None
+        st = ft.board_subtree() if (fused and algo == "CFRPlus") else None
+        if st is not None:
+            d = nat.PrlSubtree()
+            d.n_local, d.chance_node = st["n_local"], st["chance_node"]
+            d.n_boards_local, d.first_board = st["n_boards_local"], st["first_board"]
+            for i in range(st["n_local"]):
+                d.node_base[i], d.node_m[i], d.node_k[i] = st["node_base"][i], st["node_m"][i], st["node_k"][i]
+                d.kind[i], d.parent[i], d.first_child[i] = st["kind"][i], st["parent"][i], st["first_child"][i]
+                d.n_children[i], d.acted_last[i], d.pot[i] = st["n_children"][i], st["acted_last"][i], st["pot"][i]
+            self._sub, self._chance_level = d, st["chance_level"]
+        self._reach_stale = False  # fused sweeps do not maintain the reach rows of post-deal nodes
+
+    def reset(self):
+        super().reset()  # includes a full reach pass
+        self._reach_stale = False
 
     # ---- the one collective of the path
     def _allreduce_chance_sums(self, bufs, level, arrays):
@@ -84,7 +103,8 @@ class ShardedCFRSolver(CFRSolver):
                 dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
             self.n_allreduce += 1
 
-    def _value_sweep(self, bufs, mask, with_br, algo, upd_p, modes):
+    def _value_sweep(self, bufs, mask, with_br, algo, upd_p, modes, top=None):
+        """bottom-up sweep from level `top` (default: the deepest) to the root"""
         tree, buf = C.byref(self.dtree.desc), C.byref(bufs.desc)
 
         def levels(hi, lo, phase):
@@ -92,8 +112,10 @@ class ShardedCFRSolver(CFRSolver):
                      nat.modes(*modes), hi, lo, phase, _stream())
 
         arrays = [2 * p + k for p in (0, 1) if mask & (1 << p) for k in ((0, 1) if with_br else (0,))]
-        hi = self.ft.n_levels - 1
+        hi = self.ft.n_levels - 1 if top is None else top
         for d in sorted(self._chance_levels, reverse=True):
+            if d > hi:
+                continue
             if hi > d:
                 levels(hi, d + 1, 0)
             levels(d, d, 1)
@@ -107,12 +129,25 @@ class ShardedCFRSolver(CFRSolver):
         tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
         for _ in range(n):
             for p in (0, 1):
-                self._value_sweep(self.bufs, 1 << p, False, self.algo, p, self.modes)
-                self.modes[p] = nat.STRAT_F32
-                nat.call("prl_reach_update", tree, buf, self.algo, p, self.iter_counter, self.delay, _stream())
+                if self._sub is not None and self.modes[1 - p] == nat.STRAT_F32:
+                    # fused path: board subtrees in shared memory, then the trunk levels with the usual kernels
+                    nat.call("prl_cfr_plus_board_sweep", tree, buf, C.byref(self._sub), p, self.iter_counter,
+                             self.delay, nat.modes(*self.modes), _stream())
+                    self._value_sweep(self.bufs, 1 << p, False, self.algo, p, self.modes, top=self._chance_level)
+                    self.modes[p] = nat.STRAT_F32
+                    nat.call("prl_reach_levels", tree, buf, 1 << p, self.algo, p, self.iter_counter, self.delay,
+                             nat.modes(*self.modes), 0, self._chance_level, _stream())
+                    self._reach_stale = True
+                else:
+                    self._value_sweep(self.bufs, 1 << p, False, self.algo, p, self.modes)
+                    self.modes[p] = nat.STRAT_F32
+                    nat.call("prl_reach_update", tree, buf, self.algo, p, self.iter_counter, self.delay, _stream())
             self.iter_counter += 1
 
     def exploitability_current(self):
+        if self._reach_stale:
+            self.ops.reach_pass(self.modes)
+            self._reach_stale = False
         self._value_sweep(self.bufs, 3, True, -1, -1, self.modes)
         return self._metric(self.ops.root_exploitability())
 

@@ -305,6 +305,7 @@ class FlatTree:
         self.kind, self.acted_last, self.action = kind, acted_last, action
         self.pot, self.round, self.board, self.abs_id = pot, rnd, board, abs_id
         self.cdepth = cdepth  # number of chance deals above the node
+        self._abs_base, self._abs_m, self._abs_k = a_base, a_m, a_k  # flat id of (abstract node a, board j) = base + j*m + k
         self.stack, self.bet = stack, bet
         self.dfs = dfs
         self.slot, self.first_slot = slot, first_slot
@@ -332,6 +333,28 @@ class FlatTree:
         # board == -1 means chance depth 0 -> global board 0 (empty)
         out[m] = bc[self.board[m]]
         return out
+
+    def board_subtree(self):
+        """Description of the post-deal subtree shared by all boards of a single-chance-layer tree (prl_subtree_t):
+        local nodes = abstract nodes below the deal in breadth-first order.  None if the tree has another shape."""
+        A = self.abs_nodes
+        ch = [i for i, n in enumerate(A) if n.kind == KIND_CHANCE]
+        if len(ch) != 1 or max(n.cdepth for n in A) != 1:
+            return None
+        local = sorted([i for i, n in enumerate(A) if n.cdepth == 1], key=lambda i: (A[i].depth, i))
+        if len(local) > 16:
+            return None
+        loc = {a: i for i, a in enumerate(local)}
+        chance_flat = int(self._abs_base[ch[0]] + self._abs_k[ch[0]])
+        return dict(
+            n_local=len(local), chance_node=chance_flat, chance_level=int(A[ch[0]].depth),
+            n_boards_local=int(self.n_children[chance_flat]), first_board=int(self.board[self.first_child[chance_flat]]),
+            node_base=[int(self._abs_base[a]) for a in local], node_m=[int(self._abs_m[a]) for a in local],
+            node_k=[int(self._abs_k[a]) for a in local], kind=[int(A[a].kind) for a in local],
+            parent=[loc.get(A[a].parent, -1) for a in local],
+            first_child=[loc[A[a].children[0]] if A[a].children else -1 for a in local],
+            n_children=[len(A[a].children) for a in local], acted_last=[int(A[a].acted_last) for a in local],
+            pot=[float(A[a].pot) for a in local])
 
     def work_order(self):
         """(order, level_nonterm): per level the node ids sorted by (kind, n_children), non-terminals first, so that

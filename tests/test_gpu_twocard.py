@@ -94,7 +94,7 @@ def test_sharded_schedule_single_rank_equals_plain_solver():
     ft = fhp_tree(spec)
     g = games.Flop5Holdem
     args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=[1.0])
-    a, b = CFRSolver(ft, "CFRPlus"), ShardedCFRSolver(g, args, spec, "CFRPlus")
+    a, b = CFRSolver(ft, "CFRPlus"), ShardedCFRSolver(g, args, spec, "CFRPlus", fused=False)
     for _ in range(3):
         a.iteration(1)
         b.iteration(1)
@@ -133,3 +133,27 @@ def test_multi_street_subgame_matches_oracle():
         assert abs(a - b) <= 5e-5 * abs(b), (t, a, b)
         a, b = s.exploitability_average(), c.exploitability_average()
         assert abs(a - b) <= 5e-5 * abs(b), (t, a, b)
+
+
+def test_fused_board_sweep_matches_level_sweeps():
+    """The fused per-board CFR+ kernel (node vectors in shared memory) against the level-synchronous kernels."""
+    from pokerrl_b200.distributed import ShardedCFRSolver
+    from pokerrl_b200.game import games
+    spec = random_board_spec(40, 11)
+    g = games.Flop5Holdem
+    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=[1.0])
+    a = ShardedCFRSolver(g, args, spec, "CFRPlus", fused=False)
+    b = ShardedCFRSolver(g, args, spec, "CFRPlus", fused=True)
+    assert b._sub is not None and a._sub is None
+    for t in range(6):
+        a.iteration(1)
+        b.iteration(1)
+        # regrets agree to float32 round-off (strategies are not compared element-wise: regret matching turns a
+        # round-off-sized regret into a pure strategy, SURVEY.md appendix C)
+        x = a.bufs.regret.cpu().numpy().astype(np.float64)
+        y = b.bufs.regret.cpu().numpy().astype(np.float64)
+        _close("regret it%d" % t, y, x, tol=5e-5)
+        ea, eb = a.exploitability_current(), b.exploitability_current()
+        assert abs(ea - eb) <= 5e-5 * abs(ea), (t, ea, eb)
+        ea, eb = a.exploitability_average(), b.exploitability_average()
+        assert abs(ea - eb) <= 5e-5 * abs(ea), (t, ea, eb)
