@@ -368,29 +368,29 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
         // taken in the board's strength order: rp[c][i] = mass of the i weakest live hands containing card c
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
         const int row_len = n_deck - 1;
-        // one THREAD per card row, sequential running sum: ~4 instructions per element instead of a 5-step warp scan
-        // per row (the terminal kernel is instruction-issue bound, profiles/r01_c_fhp_kernels.md); the loads of a row are
-        // independent of the running sum, so they pipeline.
-        if (threadIdx.x < n_deck) {
-            const int cc = threadIdx.x;
-            float* row = rp + cc * kRowStride;
-            float run = 0.0f;
-            row[0] = 0.0f;
+        // one WARP per card row: two elements per lane, warp-shuffle inclusive scan (measured on the full game: the
+        // one-thread-per-row sequential variant is ~7 % slower end to end)
+        for (int cc = warp; cc < n_deck; cc += n_warps) {
+            float v0 = 0.0f, v1 = 0.0f;
             if (row_order) {
-                const int16_t* ord = row_order + cc * row_len;
-#pragma unroll 4
-                for (int i = 0; i < row_len; ++i) {
-                    const int hh = ord[i];
-                    run += (hh >= 0) ? ro[hh] : 0.0f;
-                    row[i + 1] = run;
-                }
-            } else {  // no board: any fixed order of the row (pre-deal fold terminals only need the row totals)
-#pragma unroll 4
-                for (int i = 0; i < row_len; ++i) {
-                    run += ro[pair_index(cc, i + (i >= cc), n_deck)];
-                    row[i + 1] = run;
-                }
+                const int h0 = (lane < row_len) ? row_order[cc * row_len + lane] : -1;
+                const int h1 = (lane + 32 < row_len) ? row_order[cc * row_len + lane + 32] : -1;
+                v0 = (h0 >= 0) ? ro[h0] : 0.0f;
+                v1 = (h1 >= 0) ? ro[h1] : 0.0f;
+            } else {  // no complete board: any fixed order of the row (fold terminals only need the row totals)
+                const int x0 = lane + (lane >= cc), x1 = lane + 32 + (lane + 32 >= cc);
+                v0 = (lane < row_len) ? ro[pair_index(cc, x0, n_deck)] : 0.0f;
+                v1 = (lane + 32 < row_len) ? ro[pair_index(cc, x1, n_deck)] : 0.0f;
             }
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t0 = __shfl_up_sync(0xffffffffu, v0, o), t1 = __shfl_up_sync(0xffffffffu, v1, o);
+                if (lane >= o) { v0 += t0; v1 += t1; }
+            }
+            v1 += __shfl_sync(0xffffffffu, v0, 31);
+            float* row = rp + cc * kRowStride;
+            if (lane == 0) row[0] = 0.0f;
+            if (lane < row_len) row[lane + 1] = v0;
+            if (lane + 32 < row_len) row[lane + 33] = v1;
         }
         __syncthreads();
         if (kind == PRL_KIND_FOLD) {
