@@ -467,6 +467,10 @@ def main():
                     "chance_*_kernel over all %d levels (terminal2_kernel is the largest share, see profiles/)" % st["levels"],
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": psrc,
                     "algorithmic_bytes_per_sweep": vb, "sweep_ms": vm, "traffic": None,
+                    "traffic_note": "no full-game ncu --set full capture (110 GB resident; replay save/restore); the 20 000-"
+                    "board capture in profiles/r01_c_fhp_kernels.md has terminal2_kernel at 22.2 KB DRAM per terminal row "
+                    "(algorithmic 10.6 KB rows + per-board tables that mostly hit L2), value2_kernel 5.1 KB and "
+                    "reach2_kernel<true> 7.8 KB per node: no re-read excess over the algorithmic bytes",
                     "reach_sweep": {"kernel": "reach2_kernel<true> x %d levels" % st["levels"], "algorithmic_bytes": rb,
                                     "sweep_ms": rm, "achieved": rb / (rm * 1e-3) / 1e9, "frac": rb / (rm * 1e-3) / 1e9 / peak}}
     else:

@@ -96,6 +96,15 @@ typedef struct {
     int32_t n_sym;               /* hand permutations summed at chance parents (24 suit permutations with isomorphism, else 0/1) */
     const int16_t* sym_perm;     /* DEVICE int16[n_sym][n_range] */
     float eq_const;              /* opponent-hand normaliser C(deck,2)/C(deck-2,2) (ValueFiller.py:19 generalised) */
+    const void* board_hand_rec;  /* DEVICE int16[n_boards][n_range][8] or NULL: the showdown tables of one hand packed for a
+                                    single 16-byte load: {gs, ge, c1*53 + row_pos[0], c1*53 + row_pos[2],
+                                    c2*53 + row_pos[1], c2*53 + row_pos[3], 0, 0} (53 = row stride of the card-row
+                                    prefix array in shared memory); NULL: the separate tables above are read */
+    const void* node_rec2;       /* DEVICE int32[n_nodes][4] or NULL: {parent, slot, first slot of the parent's children,
+                                    kind(parent) | n_children(parent) << 8} - the top-down sweep reads a node's structure
+                                    with one 16-byte load; NULL: parent / slot / first_child / n_children / kind are read */
+    const void* work_rec2;       /* DEVICE int32[n_nodes][4] or NULL, indexed like `order`: {node, first child, first slot of
+                                    the children, kind | n_children << 8} for the bottom-up sweep over decision nodes */
 } prl_tree_t;
 
 /* Caller-owned work buffers. */

@@ -15,6 +15,7 @@
 // would only add work - see DESIGN.md §6.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pokerrl_b200.h"
 #include "prl_common.cuh"
@@ -235,6 +236,208 @@ __global__ void __launch_bounds__(kVecThreads) value2_kernel(const Ctx2 c) {
     }
 }
 
+// ---- v2 row kernels: one CTA per node (ceil(R / 4) threads rounded up to a warp), node structure from ONE 16-byte
+// record instead of a chain of dependent loads (parent -> first_child[parent] -> slot[...] -> rows)
+constexpr int kRowThreadsMax = 352;  // 1326 hands / 4 per thread = 332 -> 11 warps
+
+// node_rec2[n] = {parent, slot of n, first slot of the parent's children, kind(parent) | n_children(parent) << 8}
+template <bool UPDATE_AVG>
+__global__ void __launch_bounds__(kRowThreadsMax, 4) reach2_kernel_v2(const Ctx2 c) {
+    const int ld = c.T.ld, R = c.T.n_range;
+    const int n = c.lo + blockIdx.x;
+    const int h0 = 4 * threadIdx.x;
+    if (h0 >= R) return;
+    const size_t N = (size_t)c.T.n_nodes;
+    const int4 rec = reinterpret_cast<const int4*>(c.T.node_rec2)[n];
+    const int par = rec.x, slot = rec.y, fs = rec.z, pk = rec.w & 0xff, A = rec.w >> 8;
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {
+        if (!(c.mask & (1 << q))) continue;
+        float* reach_q = c.B.reach + (size_t)q * N * ld;
+        F4 r;
+        if (par < 0) {  // PublicTree.py:122-124; a sub-game root that already shows a board zeroes the blocked hands
+            const int b = c.T.board[n];
+            const unsigned long long bm = (b >= 0) ? c.T.board_mask[b] : 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r.v[i] = (h0 + i < R && !hand_blocked(c.T, h0 + i, bm)) ? 1.0f / (float)R : 0.0f;
+        } else {
+            const F4 rp = ld4(reach_q + (size_t)par * ld + h0);
+            if (pk == PRL_KIND_CHANCE) {  // the deal multiplies both rows and zeroes hands holding a board card
+                const int b = c.T.board[n];
+                const unsigned long long bm = c.T.board_mask[b];
+                const float pr = c.T.board_prob[b];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r.v[i] = (h0 + i < R && !hand_blocked(c.T, h0 + i, bm)) ? rp.v[i] * pr : 0.0f;
+            } else if (pk == q) {
+                const F4 s = strat4(c, c.mode[q], slot, fs, A, h0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r.v[i] = s.v[i] * rp.v[i];
+                if (UPDATE_AVG && q == c.upd_p) {
+                    float* ap = (float*)c.B.avg + (size_t)slot * ld + h0;
+                    if (c.algo == PRL_ALGO_CFR_PLUS) {  // CFRPlus.py:65-87 (float table)
+                        if (c.iter >= c.delay) {
+                            F4 a = ld4(ap);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) a.v[i] = c.m_old * a.v[i] + c.m_new * s.v[i];
+                            st4(ap, a);
+                        }
+                    } else {
+                        F4 a = ld4(ap);
+                        const float w = (c.algo == PRL_ALGO_LINEAR) ? (float)(c.iter + 1) : 1.0f;  // LinearCFR.py:56-61
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a.v[i] = a.v[i] + r.v[i] * w;  // VanillaCFR.py:57-62
+                        st4(ap, a);
+                    }
+                }
+            } else {
+                r = rp;
+            }
+        }
+        st4(reach_q + (size_t)n * ld + h0, r);
+    }
+}
+
+// regrets + regret matching of the seat's own node with the A child rows held in registers (each row is loaded once);
+// same operations in the same order as the loops of value2_kernel -> identical results
+template <int A>
+__device__ __forceinline__ F4 own_node_update(const Ctx2& c, int fs, int h0, const float* ecol) {
+    const size_t ld = c.T.ld;
+    float* rcol = c.B.regret + (size_t)fs * ld + h0;
+    float* scol = c.B.strat + (size_t)fs * ld + h0;
+    F4 e[A], rg[A];
+#pragma unroll
+    for (int k = 0; k < A; ++k) e[k] = ld4(ecol + (size_t)k * ld);
+#pragma unroll
+    for (int k = 0; k < A; ++k) rg[k] = ld4(rcol + (size_t)k * ld);
+    F4 v = splat(0.0f);
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        const F4 s = ld4(scol + (size_t)k * ld);  // the seat's current strategy (PRL_STRAT_F32)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v.v[i] += s.v[i] * e[k].v[i];
+    }
+    const float w = (float)(c.iter + 1);
+    F4 ssum = splat(0.0f);
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float d = e[k].v[i] - v.v[i];
+            float r;
+            if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rg[k].v[i], 0.0f);
+            else if (c.algo == PRL_ALGO_LINEAR) r = w * d + rg[k].v[i];
+            else r = d + rg[k].v[i];
+            rg[k].v[i] = r;
+            ssum.v[i] += fmaxf(r, 0.0f);
+        }
+    }
+    const float uni = 1.0f / (float)A;
+    F4 inv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) inv.v[i] = (ssum.v[i] > 0.0f) ? 1.0f / ssum.v[i] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        F4 st;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st.v[i] = (ssum.v[i] > 0.0f) ? fmaxf(rg[k].v[i], 0.0f) * inv.v[i] : uni;
+        st4(rcol + (size_t)k * ld, rg[k]);
+        st4(scol + (size_t)k * ld, st);
+    }
+    return v;
+}
+
+// work_rec2[t] = {node, first child, first slot of the children, kind | n_children << 8} of work-list entry t
+template <bool WITH_BR, bool UPDATE>
+__global__ void __launch_bounds__(kRowThreadsMax, 3) value2_kernel_v2(const Ctx2 c) {
+    const int ld = c.T.ld;
+    const int h0 = 4 * threadIdx.x;
+    if (h0 >= c.T.n_range) return;
+    const int4 rec = reinterpret_cast<const int4*>(c.T.work_rec2)[c.lo + blockIdx.x];
+    const int n = rec.x, fc = rec.y, fs = rec.z, kind = rec.w & 0xff, A = rec.w >> 8;
+    const size_t N = (size_t)c.T.n_nodes;
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        if (!(c.mask & (1 << p))) continue;
+        float* ev_p = c.B.ev + (size_t)p * N * ld;
+        float* evbr_p = WITH_BR ? c.B.ev_br + (size_t)p * N * ld : nullptr;
+        const float* ecol = ev_p + (size_t)fc * ld + h0;
+        F4 v = splat(0.0f), vbr = splat(0.0f);
+        if (kind != p) {  // the other seat acts: sums over children
+            for (int k = 0; k < A; ++k) {
+                const F4 e = ld4(ecol + (size_t)k * ld);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v.v[i] += e.v[i];
+            }
+            if (WITH_BR)
+                for (int k = 0; k < A; ++k) {
+                    const F4 e = ld4(evbr_p + (size_t)(fc + k) * ld + h0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vbr.v[i] += e.v[i];
+                }
+        } else if (UPDATE && p == c.upd_p && A >= 2 && A <= 4 && c.mode[p] == PRL_STRAT_F32) {
+            if (A == 2) v = own_node_update<2>(c, fs, h0, ecol);
+            else if (A == 3) v = own_node_update<3>(c, fs, h0, ecol);
+            else v = own_node_update<4>(c, fs, h0, ecol);
+        } else {
+            const int m = c.mode[p];
+            for (int k = 0; k < A; ++k) {
+                const F4 e = ld4(ecol + (size_t)k * ld);
+                const F4 s = strat4(c, m, fs + k, fs, A, h0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v.v[i] += s.v[i] * e.v[i];
+            }
+            if (WITH_BR) {
+                vbr = ld4(evbr_p + (size_t)fc * ld + h0);
+                for (int k = 1; k < A; ++k) {
+                    const F4 e = ld4(evbr_p + (size_t)(fc + k) * ld + h0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vbr.v[i] = fmaxf(vbr.v[i], e.v[i]);
+                }
+            }
+            if (UPDATE && p == c.upd_p) {  // any other fan-out: rows re-read from L1 / L2
+                float* rcol = c.B.regret + (size_t)fs * ld + h0;
+                float* scol = c.B.strat + (size_t)fs * ld + h0;
+                const float w = (float)(c.iter + 1);
+                F4 ssum = splat(0.0f);
+                for (int k = 0; k < A; ++k) {
+                    const F4 e = ld4(ecol + (size_t)k * ld), rg = ld4(rcol + (size_t)k * ld);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float d = e.v[i] - v.v[i];
+                        float r;
+                        if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rg.v[i], 0.0f);
+                        else if (c.algo == PRL_ALGO_LINEAR) r = w * d + rg.v[i];
+                        else r = d + rg.v[i];
+                        ssum.v[i] += fmaxf(r, 0.0f);
+                    }
+                }
+                const float uni = 1.0f / (float)A;
+                F4 inv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) inv.v[i] = (ssum.v[i] > 0.0f) ? 1.0f / ssum.v[i] : 0.0f;
+                for (int k = 0; k < A; ++k) {
+                    const F4 e = ld4(ecol + (size_t)k * ld);
+                    F4 rg = ld4(rcol + (size_t)k * ld), st;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float d = e.v[i] - v.v[i];
+                        float r;
+                        if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rg.v[i], 0.0f);
+                        else if (c.algo == PRL_ALGO_LINEAR) r = w * d + rg.v[i];
+                        else r = d + rg.v[i];
+                        rg.v[i] = r;
+                        st.v[i] = (ssum.v[i] > 0.0f) ? fmaxf(r, 0.0f) * inv.v[i] : uni;
+                    }
+                    st4(rcol + (size_t)k * ld, rg);
+                    st4(scol + (size_t)k * ld, st);
+                }
+            }
+        }
+        st4(ev_p + (size_t)n * ld + h0, v);
+        if (WITH_BR) st4(evbr_p + (size_t)n * ld + h0, vbr);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ chance nodes (bottom-up)
 // stage 1: block (chance entry j, chunk) sums board_mult * child rows of its chunk -> workspace[arr][j][chunk][h]
 // stage 2: thread (j, h): sums the chunks in order -> workspace W[arr][j][h]
@@ -327,8 +530,9 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 32 floats *
 }
 
 // one CTA per terminal node; ValueFiller.py:34-62, 103-158 generalised
+// v1 (kept for A/B measurements, PRL_TERMINAL_V1=1): one warp per card row, warp-shuffle scans
 template <bool WITH_BR>
-__global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
+__global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v1(const Ctx2 c) {
     extern __shared__ float smem[];
     const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck;
     float* ro = smem;                      // [R]      opponent reach row
@@ -462,6 +666,187 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
     }
 }
 
+// v2: same arithmetic with fewer instructions and barriers per terminal row
+//   - card rows are scanned by QUADS (4 lanes x <= 16 consecutive row entries, sequential in registers, then a 2-step
+//     quad scan) instead of one warp per row: 52 rows fit one pass of 208 threads
+//   - every prefix array is stored CENTRED,  E[i] = (mass of the i weakest) - total / 2,  so that
+//     (strictly weaker) - (strictly stronger) = E[gs] + E[ge]  without loading the totals
+//   - the scatter into strength order happens while the row is loaded; fold rows skip scans, showdown rows skip the sum
+//   - optional packed per-hand record (prl_tree_t.board_hand_rec): {gs, ge, 4 offsets into the card-row prefix array}
+//     in one 16-byte load instead of five narrow ones
+constexpr int kSegMax = 16;  // row entries per quad lane: ceil((n_deck - 1) / 4) <= 16
+template <bool WITH_BR>
+__global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
+    extern __shared__ float smem[];
+    const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck;
+    float* ro = smem;                      // [R]      opponent reach row
+    float* srt = ro + R;                   // [R + 1]  reach in strength order, then its centred exclusive prefix sums
+    float* red = srt + R + 1;              // [32]
+    float* wsum = red + 32;                // [kTermThreads / 32]
+    float* rp = wsum + kTermThreads / 32;  // [n_deck][kRowStride] centred prefix sums of every card row (fold: [n_deck] sums)
+    const int n = c.T.order[c.lo + blockIdx.x];
+    const int kind = c.T.kind[n];
+    const int b = c.T.board[n];
+    const size_t N = (size_t)c.T.n_nodes;
+    const float scale = c.T.eq_const * c.T.pot[n] * 0.5f;
+    const bool fold = kind == PRL_KIND_FOLD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int row_len = n_deck - 1, seg = (row_len + 3) >> 2;
+    const int qj = threadIdx.x & 3;
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        if (!(c.mask & (1 << p))) continue;
+        const float* ro_g = c.B.reach + ((size_t)(1 - p) * N + n) * ld;
+        float* ev_p = c.B.ev + ((size_t)p * N + n) * ld;
+        float* evbr_p = WITH_BR ? c.B.ev_br + ((size_t)p * N + n) * ld : nullptr;
+        __syncthreads();  // shared arrays are reused by the second seat
+        if (fold) {
+            float part = 0.0f;
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const float r = ro_g[h];
+                ro[h] = r;
+                part += r;
+            }
+            const float T = block_sum(part, red);  // includes the barrier that publishes ro[]
+            // per-card sums: quad lane qj adds entries [qj * seg, qj * seg + seg) of the card's row
+            for (int base = 0; base < n_deck; base += blockDim.x >> 2) {
+                const int cc = base + (threadIdx.x >> 2);
+                float run = 0.0f;
+                if (cc < n_deck) {
+                    for (int i = 0; i < seg; ++i) {
+                        const int idx = qj * seg + i;
+                        if (idx < row_len) run += ro[pair_index(cc, idx + (idx >= cc), n_deck)];
+                    }
+                }
+                run += __shfl_xor_sync(0xffffffffu, run, 1);
+                run += __shfl_xor_sync(0xffffffffu, run, 2);
+                if (cc < n_deck && qj == 0) rp[cc] = run;
+            }
+            __syncthreads();
+            const float sgn = (c.T.acted_last[n] == p) ? -scale : scale;
+            const unsigned long long bmask = (b >= 0) ? c.T.board_mask[b] : 0ull;
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
+                float v = (T - rp[c1] - rp[c2] + ro[h]) * sgn;
+                if (((bmask >> c1) | (bmask >> c2)) & 1ull) v = 0.0f;
+                ev_p[h] = v;
+                if (WITH_BR) evbr_p[h] = v;
+            }
+            continue;
+        }
+        // ---- showdown on a complete board (strength tables exist)
+        const int16_t* pos_tab = c.T.board_pos + (size_t)b * R;
+        const int16_t* row_order = c.T.board_row_order + (size_t)b * n_deck * row_len;
+        for (int i = threadIdx.x; i <= R; i += blockDim.x) srt[i] = 0.0f;
+        __syncthreads();
+        // 1. load the row, scattering it into strength order (pos is a permutation of the live hands: deterministic)
+        for (int h = threadIdx.x; h < R; h += blockDim.x) {
+            const float r = ro_g[h];
+            const int ps = pos_tab[h];
+            ro[h] = r;
+            if (ps >= 0) srt[ps] = r;
+        }
+        __syncthreads();
+        // 2a. centred prefix sums of every card row in strength order: rp[c][i] = mass of the i weakest live hands
+        //     holding card c, minus half the row's mass
+        for (int base = 0; base < n_deck; base += blockDim.x >> 2) {
+            const int cc = base + (threadIdx.x >> 2);
+            const bool live = cc < n_deck;
+            float inc[kSegMax];
+            float run = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kSegMax; ++i) {
+                const int idx = qj * seg + i;
+                float v = 0.0f;
+                if (live && i < seg && idx < row_len) {
+                    const int hh = row_order[cc * row_len + idx];
+                    if (hh >= 0) v = ro[hh];
+                }
+                run += v;
+                inc[i] = run;
+            }
+            float sc = run;  // inclusive scan over the quad
+            float t = __shfl_up_sync(0xffffffffu, sc, 1, 4);
+            if (qj >= 1) sc += t;
+            t = __shfl_up_sync(0xffffffffu, sc, 2, 4);
+            if (qj >= 2) sc += t;
+            const float half = 0.5f * __shfl_sync(0xffffffffu, sc, 3, 4);
+            const float off = (sc - run) - half;
+            if (live) {
+                float* row = rp + cc * kRowStride;
+                if (qj == 0) row[0] = -half;
+#pragma unroll
+                for (int i = 0; i < kSegMax; ++i) {
+                    const int idx = qj * seg + i;
+                    if (i < seg && idx < row_len) row[idx + 1] = off + inc[i];
+                }
+            }
+        }
+        // 2b. centred exclusive prefix sums over srt[0..R] (each thread owns a contiguous segment, then a block scan)
+        const int per = (R + 1 + blockDim.x - 1) / blockDim.x;
+        const int i0 = threadIdx.x * per, i1 = min(R + 1, i0 + per);
+        float loc = 0.0f;
+        for (int i = i0; i < i1; ++i) loc += srt[i];
+        float incw = loc;  // inclusive scan of the per-thread sums within the warp
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incw, o);
+            if (lane >= o) incw += t;
+        }
+        if (lane == 31) wsum[warp] = incw;
+        __syncthreads();
+        float before = 0.0f, total = 0.0f;  // every thread adds the warp totals itself (fixed order)
+        for (int w = 0; w < n_warps; ++w) {
+            const float x = wsum[w];
+            if (w < warp) before += x;
+            total += x;
+        }
+        float run = (incw - loc) + before - 0.5f * total;
+        for (int i = i0; i < i1; ++i) {
+            const float x = srt[i];
+            srt[i] = run;
+            run += x;
+        }
+        __syncthreads();
+        // 3. per hand: (weaker - stronger) mass over all live hands minus the same over the two card rows of the hand
+        //    (the hands that share a card with it; the hand itself ties with itself and drops out)
+        if (c.T.board_hand_rec) {
+            const uint4* rec = reinterpret_cast<const uint4*>(c.T.board_hand_rec) + (size_t)b * R;
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const uint4 q = rec[h];  // int16 x 8: gs, ge, c1 row + lt, c1 row + le, c2 row + lt, c2 row + le, 0, 0
+                const int gs = (int)(short)(q.x & 0xffffu);
+                float v = 0.0f;
+                if (gs >= 0) {
+                    const float all = srt[gs] + srt[q.x >> 16];
+                    const float rows = (rp[q.y & 0xffffu] + rp[q.y >> 16]) + (rp[q.z & 0xffffu] + rp[q.z >> 16]);
+                    v = (all - rows) * scale;
+                }
+                ev_p[h] = v;
+                if (WITH_BR) evbr_p[h] = v;
+            }
+        } else {
+            const int16_t* gs_tab = c.T.board_gs + (size_t)b * R;
+            const int16_t* ge_tab = c.T.board_ge + (size_t)b * R;
+            const uchar4* row_pos = reinterpret_cast<const uchar4*>(c.T.board_row_pos) + (size_t)b * R;
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const int gs = gs_tab[h];
+                float v = 0.0f;
+                if (gs >= 0) {
+                    const int ge = ge_tab[h];
+                    const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
+                    const uchar4 q = row_pos[h];  // {weaker in row c1, weaker in row c2, weaker-or-equal c1, c2}
+                    const float* r1 = rp + c1 * kRowStride;
+                    const float* r2 = rp + c2 * kRowStride;
+                    const float all = srt[gs] + srt[ge];
+                    const float rows = (r1[q.x] + r1[q.z]) + (r2[q.y] + r2[q.w]);
+                    v = (all - rows) * scale;
+                }
+                ev_p[h] = v;
+                if (WITH_BR) evbr_p[h] = v;
+            }
+        }
+    }
+}
+
 // ---- strength-order tables of complete boards: gs = # live hands strictly weaker, ge = # live hands weaker or equal,
 //      pos = unique position in strength order (ties by hand index); -1 for hands blocked by the board
 __global__ void __launch_bounds__(256) board_order_kernel(const int32_t* __restrict__ ranks, int n_boards, int R,
@@ -567,16 +952,34 @@ size_t term_smem(const prl_tree_t& T) {
     return sizeof(float) * ((size_t)2 * T.n_range + 1 + 64 + 32 + kTermThreads / 32 + 1 + (size_t)T.n_deck * kRowStride);
 }
 
+// threads of the one-CTA-per-node row kernels (0: range too wide, use the tiled v1 kernels)
+inline int row_threads(const prl_tree_t& T) {
+    const int t = (((T.n_range + 3) / 4) + 31) & ~31;
+    return t <= kRowThreadsMax ? t : 0;
+}
+
+// one level of the reach sweep: c.lo / c.n set by the caller
+void launch_reach_level(const Ctx2& c, bool update_avg, cudaStream_t s) {
+    const prl_tree_t& T = c.T;
+    const int rt = row_threads(T);
+    if (T.node_rec2 && rt) {
+        if (update_avg) reach2_kernel_v2<true><<<c.n, rt, 0, s>>>(c);
+        else reach2_kernel_v2<false><<<c.n, rt, 0, s>>>(c);
+    } else {
+        const dim3 g((unsigned)c.n, (unsigned)((T.n_range + 4 * kVecThreads - 1) / (4 * kVecThreads)));
+        if (update_avg) reach2_kernel<true><<<g, kVecThreads, 0, s>>>(c);
+        else reach2_kernel<false><<<g, kVecThreads, 0, s>>>(c);
+    }
+    prl::count_launch();
+}
+
 void reach_sweep2(Ctx2 c, bool update_avg, cudaStream_t s) {
     const prl_tree_t& T = c.T;
     for (int d = 0; d < T.n_levels; ++d) {
         c.lo = (int)T.level_start[d];
         c.n = (int)(T.level_start[d + 1] - T.level_start[d]);
         if (c.n == 0) continue;
-        const dim3 g((unsigned)c.n, (unsigned)((T.n_range + 4 * kVecThreads - 1) / (4 * kVecThreads)));
-        if (update_avg) reach2_kernel<true><<<g, kVecThreads, 0, s>>>(c);
-        else reach2_kernel<false><<<g, kVecThreads, 0, s>>>(c);
-        prl::count_launch();
+        launch_reach_level(c, update_avg, s);
     }
 }
 
@@ -589,8 +992,12 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
     if (!smem_set) {
         cudaFuncSetAttribute(terminal2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        cudaFuncSetAttribute(terminal2_kernel_v1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        cudaFuncSetAttribute(terminal2_kernel_v1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         smem_set = true;
     }
+    const char* v1_env = getenv("PRL_TERMINAL_V1");  // A/B switch, read per call
+    const bool use_v1 = v1_env && v1_env[0] == '1';
     int arr_mask = 0;
     for (int p = 0; p < 2; ++p)
         if (c.mask & (1 << p)) arr_mask |= (1 << (2 * p)) | (with_br ? (2 << (2 * p)) : 0);
@@ -601,17 +1008,29 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
         if (n_term > 0 && chance_phase != 2) {
             c.lo = lo + n_nonterm;
             c.n = n_term;
-            if (with_br) terminal2_kernel<true><<<n_term, kTermThreads, tsm, s>>>(c);
-            else terminal2_kernel<false><<<n_term, kTermThreads, tsm, s>>>(c);
+            if (use_v1) {
+                if (with_br) terminal2_kernel_v1<true><<<n_term, kTermThreads, tsm, s>>>(c);
+                else terminal2_kernel_v1<false><<<n_term, kTermThreads, tsm, s>>>(c);
+            } else {
+                if (with_br) terminal2_kernel<true><<<n_term, kTermThreads, tsm, s>>>(c);
+                else terminal2_kernel<false><<<n_term, kTermThreads, tsm, s>>>(c);
+            }
             prl::count_launch();
         }
         if (n_dec > 0 && chance_phase != 2) {
             c.lo = lo;
             c.n = n_dec;
-            const dim3 g((unsigned)n_dec, (unsigned)((T.n_range + 4 * kVecThreads - 1) / (4 * kVecThreads)));
-            if (update) value2_kernel<false, true><<<g, kVecThreads, 0, s>>>(c);
-            else if (with_br) value2_kernel<true, false><<<g, kVecThreads, 0, s>>>(c);
-            else value2_kernel<false, false><<<g, kVecThreads, 0, s>>>(c);
+            const int rt = row_threads(T);
+            if (T.work_rec2 && rt) {
+                if (update) value2_kernel_v2<false, true><<<n_dec, rt, 0, s>>>(c);
+                else if (with_br) value2_kernel_v2<true, false><<<n_dec, rt, 0, s>>>(c);
+                else value2_kernel_v2<false, false><<<n_dec, rt, 0, s>>>(c);
+            } else {
+                const dim3 g((unsigned)n_dec, (unsigned)((T.n_range + 4 * kVecThreads - 1) / (4 * kVecThreads)));
+                if (update) value2_kernel<false, true><<<g, kVecThreads, 0, s>>>(c);
+                else if (with_br) value2_kernel<true, false><<<g, kVecThreads, 0, s>>>(c);
+                else value2_kernel<false, false><<<g, kVecThreads, 0, s>>>(c);
+            }
             prl::count_launch();
         }
         if (n_chance > 0) {
@@ -966,10 +1385,7 @@ extern "C" int prl_reach_levels(const prl_tree_t* tree, const prl_buffers_t* buf
         c.lo = (int)T.level_start[d];
         c.n = (int)(T.level_start[d + 1] - T.level_start[d]);
         if (c.n == 0) continue;
-        const dim3 g((unsigned)c.n, (unsigned)((T.n_range + 4 * kVecThreads - 1) / (4 * kVecThreads)));
-        if (algo >= 0) reach2_kernel<true><<<g, kVecThreads, 0, (cudaStream_t)stream>>>(c);
-        else reach2_kernel<false><<<g, kVecThreads, 0, (cudaStream_t)stream>>>(c);
-        prl::count_launch();
+        launch_reach_level(c, algo >= 0, (cudaStream_t)stream);
     }
     return prl::check(cudaGetLastError(), "prl_reach_levels");
 }

@@ -25,6 +25,30 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def structure_records(ft, order):
+    """16-byte structure records of the two-card sweeps (prl_tree_t.node_rec2 / work_rec2), host side.
+    node record  n: {parent, slot, first slot of the parent's children, kind(parent) | n_children(parent) << 8}
+    work record  t: {node = order[t], its first child, first slot of its children, kind | n_children << 8}"""
+    par = ft.parent.astype(np.int64)
+    has_par = par >= 0
+    sp_ = np.where(has_par, par, 0)
+    fc_par = ft.first_child[sp_].astype(np.int64)
+    nrec = np.zeros((ft.n_nodes, 4), np.int32)
+    nrec[:, 0] = par
+    nrec[:, 1] = ft.slot
+    nrec[:, 2] = np.where(has_par, ft.slot[np.maximum(fc_par, 0)], 0)
+    nrec[:, 3] = np.where(has_par, ft.kind[sp_].astype(np.int64) | (ft.n_children[sp_].astype(np.int64) << 8), 0)
+    order = np.asarray(order).astype(np.int64)
+    fc = ft.first_child[order].astype(np.int64)
+    nonterm = (ft.n_children[order] > 0) & (fc >= 0)
+    wrec = np.zeros((ft.n_nodes, 4), np.int32)
+    wrec[:, 0] = order
+    wrec[:, 1] = np.where(nonterm, fc, 0)
+    wrec[:, 2] = np.where(nonterm, ft.slot[np.maximum(fc, 0)], 0)
+    wrec[:, 3] = ft.kind[order].astype(np.int64) | (ft.n_children[order].astype(np.int64) << 8)
+    return nrec, wrec
+
+
 class DeviceTree:
     """FlatTree uploaded to HBM + the prl_tree_t descriptor handed to the C ABI."""
 
@@ -126,6 +150,18 @@ class DeviceTree:
             gs[ids], ge[ids], pos[ids], row_order[ids], row_pos[ids] = g1, g2, g3, ro, rp
         self.t_board_gs, self.t_board_ge, self.t_board_pos = gs, ge, pos
         self.t_board_row_order, self.t_board_row_pos = row_order, row_pos
+        # packed per-hand showdown record (one 16-byte load in terminal2_kernel): see prl_tree_t.board_hand_rec
+        self.t_board_hand_rec = None
+        if os.environ.get("PRL_NO_HAND_REC", "0") != "1":
+            rec = torch.zeros((nb, self.R, 8), dtype=torch.int16, device=dev)
+            row_base = self.t_hand_cards.to(torch.int16) * 53  # [R, 2]
+            for i in range(0, nb, CH):
+                sl = slice(i, min(nb, i + CH))
+                rec[sl, :, 0], rec[sl, :, 1] = gs[sl], ge[sl]
+                q = row_pos[sl].to(torch.int16)
+                rec[sl, :, 2], rec[sl, :, 3] = row_base[:, 0] + q[:, :, 0], row_base[:, 0] + q[:, :, 2]
+                rec[sl, :, 4], rec[sl, :, 5] = row_base[:, 1] + q[:, :, 1], row_base[:, 1] + q[:, :, 3]
+            self.t_board_hand_rec = rec
         sp = ft.board_spec.sym_perm
         self.t_sym_perm = up(sp, np.int16) if sp is not None else None
         dec_per_level = [int(((ft.kind[int(ft.level_start[k]):int(ft.level_start[k + 1])] <= nat.KIND_P1)).sum())
@@ -141,6 +177,15 @@ class DeviceTree:
         d.board_gs, d.board_ge, d.board_pos = gs.data_ptr(), ge.data_ptr(), pos.data_ptr()
         d.board_row_order, d.board_row_pos = row_order.data_ptr(), row_pos.data_ptr()
         d.board_complete = self.t_board_complete.data_ptr()
+        d.board_hand_rec = self.t_board_hand_rec.data_ptr() if self.t_board_hand_rec is not None else None
+        # one 16-byte structure record per node (top-down sweep) and per work-list entry (bottom-up sweep over decision
+        # nodes): see prl_tree_t.node_rec2 / work_rec2
+        self.t_node_rec2 = self.t_work_rec2 = None
+        if os.environ.get("PRL_NO_NODE_REC", "0") != "1":
+            nrec, wrec = structure_records(ft, self.t_order.cpu().numpy())
+            self.t_node_rec2, self.t_work_rec2 = up(nrec, np.int32), up(wrec, np.int32)
+        d.node_rec2 = self.t_node_rec2.data_ptr() if self.t_node_rec2 is not None else None
+        d.work_rec2 = self.t_work_rec2.data_ptr() if self.t_work_rec2 is not None else None
         d.n_sym = 0 if sp is None else int(sp.shape[0])
         d.sym_perm = self.t_sym_perm.data_ptr() if sp is not None else None
         n_deck, n_hole = rules.N_CARDS_IN_DECK, rules.N_HOLE_CARDS

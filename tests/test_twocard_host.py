@@ -47,3 +47,24 @@ def test_flat_tree_layout_two_card():
     assert len(ch) == 1 and ft.n_children[ch[0]] == nb
     kids = np.arange(ft.first_child[ch[0]], ft.first_child[ch[0]] + nb)
     assert np.array_equal(ft.board[kids], 1 + np.arange(nb))  # global board ids, 0 = the empty board
+
+
+def test_structure_records_restate_the_pointer_chains():
+    """prl_tree_t.node_rec2 / work_rec2 (pokerrl_b200/solver.py:structure_records) hold exactly what the v1 kernels read
+    through parent -> first_child -> slot chains"""
+    from pokerrl_b200.solver import structure_records
+    from twocard_common import fhp_tree, random_board_spec
+    ft = fhp_tree(random_board_spec(5, 3))
+    order, _ = ft.work_order()
+    nrec, wrec = structure_records(ft, order)
+    for n in range(ft.n_nodes):
+        p = int(ft.parent[n])
+        assert nrec[n, 0] == p and nrec[n, 1] == ft.slot[n]
+        if p >= 0:
+            assert nrec[n, 2] == ft.slot[ft.first_child[p]]
+            assert nrec[n, 3] & 0xff == ft.kind[p] and nrec[n, 3] >> 8 == ft.n_children[p]
+    for t in range(ft.n_nodes):
+        n = int(order[t])
+        assert wrec[t, 0] == n and wrec[t, 3] & 0xff == ft.kind[n] and wrec[t, 3] >> 8 == ft.n_children[n]
+        if ft.n_children[n] > 0:
+            assert wrec[t, 1] == ft.first_child[n] and wrec[t, 2] == ft.slot[ft.first_child[n]]
