@@ -530,142 +530,7 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 32 floats *
 }
 
 // one CTA per terminal node; ValueFiller.py:34-62, 103-158 generalised
-// v1 (kept for A/B measurements, PRL_TERMINAL_V1=1): one warp per card row, warp-shuffle scans
-template <bool WITH_BR>
-__global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v1(const Ctx2 c) {
-    extern __shared__ float smem[];
-    const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck;
-    float* ro = smem;                      // [R]      opponent reach row
-    float* srt = ro + R;                   // [R + 1]  reach in strength order, then its exclusive prefix sums
-    float* cs = srt + R + 1;               // [64]     per-card sums
-    float* red = cs + 64;                  // [32]
-    float* wsum = red + 32;                // [kTermThreads / 32 + 1]
-    float* rp = wsum + kTermThreads / 32 + 1;  // [n_deck][kRowStride] exclusive prefix sums of every card row (sorted)
-    const int n = c.T.order[c.lo + blockIdx.x];
-    const int kind = c.T.kind[n];
-    const int b = c.T.board[n];
-    const size_t N = (size_t)c.T.n_nodes;
-    const float K = c.T.eq_const;
-    const float half_pot = c.T.pot[n];
-    const unsigned long long bmask = (b >= 0) ? c.T.board_mask[b] : 0ull;
-    const bool complete = b >= 0 && c.T.board_complete[b];  // strength tables exist for complete boards only
-    const int16_t* gs_tab = complete ? c.T.board_gs + (size_t)b * R : nullptr;
-    const int16_t* ge_tab = complete ? c.T.board_ge + (size_t)b * R : nullptr;
-    const int16_t* pos_tab = complete ? c.T.board_pos + (size_t)b * R : nullptr;
-    const int16_t* row_order = complete ? c.T.board_row_order + (size_t)b * n_deck * (n_deck - 1) : nullptr;
-    const uchar4* row_pos = complete ? reinterpret_cast<const uchar4*>(c.T.board_row_pos) + (size_t)b * R : nullptr;
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) {
-        if (!(c.mask & (1 << p))) continue;
-        __syncthreads();
-        const float* ro_g = c.B.reach + ((size_t)(1 - p) * N + n) * ld;
-        float part = 0.0f;
-        for (int h = threadIdx.x; h < R; h += blockDim.x) {
-            const float r = ro_g[h];
-            ro[h] = r;
-            part += r;
-        }
-        const float T = block_sum(part, red);  // includes the barrier that publishes ro[]
-        float* ev_p = c.B.ev + ((size_t)p * N + n) * ld;
-        float* evbr_p = WITH_BR ? c.B.ev_br + ((size_t)p * N + n) * ld : nullptr;
-        // exclusive prefix sums of the opponent row along every card row (the n_deck - 1 hands containing one card),
-        // taken in the board's strength order: rp[c][i] = mass of the i weakest live hands containing card c
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-        const int row_len = n_deck - 1;
-        // one WARP per card row: two elements per lane, warp-shuffle inclusive scan (measured on the full game: the
-        // one-thread-per-row sequential variant is ~7 % slower end to end)
-        for (int cc = warp; cc < n_deck; cc += n_warps) {
-            float v0 = 0.0f, v1 = 0.0f;
-            if (row_order) {
-                const int h0 = (lane < row_len) ? row_order[cc * row_len + lane] : -1;
-                const int h1 = (lane + 32 < row_len) ? row_order[cc * row_len + lane + 32] : -1;
-                v0 = (h0 >= 0) ? ro[h0] : 0.0f;
-                v1 = (h1 >= 0) ? ro[h1] : 0.0f;
-            } else {  // no complete board: any fixed order of the row (fold terminals only need the row totals)
-                const int x0 = lane + (lane >= cc), x1 = lane + 32 + (lane + 32 >= cc);
-                v0 = (lane < row_len) ? ro[pair_index(cc, x0, n_deck)] : 0.0f;
-                v1 = (lane + 32 < row_len) ? ro[pair_index(cc, x1, n_deck)] : 0.0f;
-            }
-            for (int o = 1; o < 32; o <<= 1) {
-                const float t0 = __shfl_up_sync(0xffffffffu, v0, o), t1 = __shfl_up_sync(0xffffffffu, v1, o);
-                if (lane >= o) { v0 += t0; v1 += t1; }
-            }
-            v1 += __shfl_sync(0xffffffffu, v0, 31);
-            float* row = rp + cc * kRowStride;
-            if (lane == 0) row[0] = 0.0f;
-            if (lane < row_len) row[lane + 1] = v0;
-            if (lane + 32 < row_len) row[lane + 33] = v1;
-        }
-        __syncthreads();
-        if (kind == PRL_KIND_FOLD) {
-            const float sgn = (c.T.acted_last[n] == p) ? -1.0f : 1.0f;
-            for (int h = threadIdx.x; h < R; h += blockDim.x) {
-                const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
-                float e = (T - rp[c1 * kRowStride + row_len] - rp[c2 * kRowStride + row_len] + ro[h]) * sgn * K;
-                if (((bmask >> c1) | (bmask >> c2)) & 1ull) e = 0.0f;
-                const float v = e * half_pot * 0.5f;
-                ev_p[h] = v;
-                if (WITH_BR) evbr_p[h] = v;
-            }
-        } else {  // showdown on a complete board
-            // 1. scatter the row into strength order (pos is a permutation of the live hands: deterministic)
-            for (int i = threadIdx.x; i <= R; i += blockDim.x) srt[i] = 0.0f;
-            __syncthreads();
-            for (int h = threadIdx.x; h < R; h += blockDim.x) {
-                const int ps = pos_tab[h];
-                if (ps >= 0) srt[ps] = ro[h];
-            }
-            __syncthreads();
-            // 2. exclusive prefix sums over srt[0..R] (each thread owns a contiguous segment, then a block scan)
-            const int per = (R + 1 + blockDim.x - 1) / blockDim.x;
-            const int i0 = threadIdx.x * per, i1 = min(R + 1, i0 + per);
-            float loc = 0.0f;
-            for (int i = i0; i < i1; ++i) loc += srt[i];
-            float inc = loc;  // inclusive scan of the per-thread sums
-            for (int o = 1; o < 32; o <<= 1) {
-                const float t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) wsum[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                float w = (lane < n_warps) ? wsum[lane] : 0.0f;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float t = __shfl_up_sync(0xffffffffu, w, o);
-                    if (lane >= o) w += t;
-                }
-                if (lane < n_warps) wsum[lane] = w;
-            }
-            __syncthreads();
-            float run = inc - loc + (warp > 0 ? wsum[warp - 1] : 0.0f);  // exclusive prefix of this thread's segment
-            for (int i = i0; i < i1; ++i) {
-                const float x = srt[i];
-                srt[i] = run;
-                run += x;
-            }
-            __syncthreads();
-            // 3. per hand: (weaker - stronger) mass over all live hands minus the same over the two card rows of the hand
-            //    (the hands that share a card with it; the hand itself ties with itself and drops out)
-            for (int h = threadIdx.x; h < R; h += blockDim.x) {
-                const int gs = gs_tab[h];
-                float v = 0.0f;
-                if (gs >= 0) {
-                    const int ge = ge_tab[h];
-                    const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
-                    const uchar4 q = row_pos[h];  // {weaker in row c1, weaker in row c2, weaker-or-equal c1, c2}
-                    const float* r1 = rp + c1 * kRowStride;
-                    const float* r2 = rp + c2 * kRowStride;
-                    const float all = srt[gs] - (srt[R] - srt[ge]);
-                    const float rows = (r1[q.x] - (r1[row_len] - r1[q.z])) + (r2[q.y] - (r2[row_len] - r2[q.w]));
-                    v = (all - rows) * K * half_pot * 0.5f;
-                }
-                ev_p[h] = v;
-                if (WITH_BR) evbr_p[h] = v;
-            }
-        }
-    }
-}
-
+//
 // v2: same arithmetic with fewer instructions and barriers per terminal row
 //   - card rows are scanned by QUADS (4 lanes x <= 16 consecutive row entries, sequential in registers, then a 2-step
 //     quad scan) instead of one warp per row: 52 rows fit one pass of 208 threads
@@ -847,6 +712,196 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel(const Ctx2 c) {
     }
 }
 
+// v3: the v2 arithmetic with every input of a showdown row STAGED IN SHARED MEMORY BY ASYNCHRONOUS COPIES (cp.async):
+// the opponent's reach row and the board's three tables (strength positions, card-row orders, packed hand records) are
+// requested together right after ONE structure load (work_rec2), so a terminal row pays two dependent global latencies
+// (record -> everything) instead of five (order -> node fields -> reach row -> row orders -> hand records); the ncu
+// capture of v2 had 56 % of its stall samples on exactly those loads (profiles/r01_g_twocard_v2.md).
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__host__ __device__ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// shared-memory carve-up of terminal2_kernel_v3 (byte offsets, every region 16-byte aligned)
+struct TermSmem {
+    size_t rec, ro, roword, pos, srt, red, wsum, rp, total;
+    __host__ __device__ TermSmem(int R, int n_deck) {
+        rec = 0;
+        ro = rec + up16((size_t)R * 16);
+        roword = ro + up16((size_t)R * 4);
+        pos = roword + up16((size_t)n_deck * (n_deck - 1) * 2);
+        srt = pos + up16((size_t)R * 2);
+        red = srt + up16((size_t)(R + 1) * 4);
+        wsum = red + 32 * 4;
+        rp = wsum + up16((kTermThreads / 32) * 4);
+        total = rp + up16((size_t)n_deck * kRowStride * 4);
+    }
+};
+
+// work_rec2 entry of a TERMINAL work-list entry: {node, board id, pot (float bits), kind | (acted_last & 0xff) << 8}
+template <bool WITH_BR>
+__global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v3(const Ctx2 c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck;
+    const TermSmem L(R, n_deck);
+    uint4* rec_s = reinterpret_cast<uint4*>(smem_raw + L.rec);     // [R]   packed hand records of the board
+    float* ro = reinterpret_cast<float*>(smem_raw + L.ro);         // [R]   opponent reach row
+    int16_t* roword_s = reinterpret_cast<int16_t*>(smem_raw + L.roword);  // [n_deck][n_deck - 1] card rows in strength order
+    int16_t* pos_s = reinterpret_cast<int16_t*>(smem_raw + L.pos); // [R]   position in strength order
+    float* srt = reinterpret_cast<float*>(smem_raw + L.srt);       // [R + 1]
+    float* red = reinterpret_cast<float*>(smem_raw + L.red);       // [32]
+    float* wsum = reinterpret_cast<float*>(smem_raw + L.wsum);     // [kTermThreads / 32]
+    float* rp = reinterpret_cast<float*>(smem_raw + L.rp);         // [n_deck][kRowStride]
+    const int4 w = reinterpret_cast<const int4*>(c.T.work_rec2)[c.lo + blockIdx.x];
+    const int n = w.x, b = w.y, kind = w.w & 0xff, acted_last = (w.w >> 8) & 0xff;
+    const size_t N = (size_t)c.T.n_nodes;
+    const float scale = c.T.eq_const * __int_as_float(w.z) * 0.5f;
+    const bool fold = kind == PRL_KIND_FOLD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int row_len = n_deck - 1, seg = (row_len + 3) >> 2;
+    const int qj = threadIdx.x & 3;
+    if (!fold) {  // the board's tables do not depend on the seat: requested once, consumed after the first wait
+        const uint4* rec_g = reinterpret_cast<const uint4*>(c.T.board_hand_rec) + (size_t)b * R;
+        for (int h = threadIdx.x; h < R; h += blockDim.x) cp_async16(rec_s + h, rec_g + h);
+        const int32_t* ro_g32 = reinterpret_cast<const int32_t*>(c.T.board_row_order + (size_t)b * n_deck * row_len);
+        for (int i = threadIdx.x; i < n_deck * row_len / 2; i += blockDim.x)
+            cp_async4(reinterpret_cast<int32_t*>(roword_s) + i, ro_g32 + i);
+        const int32_t* pos_g32 = reinterpret_cast<const int32_t*>(c.T.board_pos + (size_t)b * R);
+        for (int i = threadIdx.x; i < R / 2; i += blockDim.x) cp_async4(reinterpret_cast<int32_t*>(pos_s) + i, pos_g32 + i);
+    }
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        if (!(c.mask & (1 << p))) continue;
+        const float* ro_g = c.B.reach + ((size_t)(1 - p) * N + n) * ld;
+        float* ev_p = c.B.ev + ((size_t)p * N + n) * ld;
+        float* evbr_p = WITH_BR ? c.B.ev_br + ((size_t)p * N + n) * ld : nullptr;
+        __syncthreads();  // shared arrays are reused by the second seat
+        if (fold) {
+            float part = 0.0f;
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const float r = ro_g[h];
+                ro[h] = r;
+                part += r;
+            }
+            const float T = block_sum(part, red);  // includes the barrier that publishes ro[]
+            for (int base = 0; base < n_deck; base += blockDim.x >> 2) {
+                const int cc = base + (threadIdx.x >> 2);
+                float run = 0.0f;
+                if (cc < n_deck) {
+                    for (int i = 0; i < seg; ++i) {
+                        const int idx = qj * seg + i;
+                        if (idx < row_len) run += ro[pair_index(cc, idx + (idx >= cc), n_deck)];
+                    }
+                }
+                run += __shfl_xor_sync(0xffffffffu, run, 1);
+                run += __shfl_xor_sync(0xffffffffu, run, 2);
+                if (cc < n_deck && qj == 0) rp[cc] = run;
+            }
+            __syncthreads();
+            const float sgn = (acted_last == p) ? -scale : scale;
+            const unsigned long long bmask = (b >= 0) ? c.T.board_mask[b] : 0ull;
+            for (int h = threadIdx.x; h < R; h += blockDim.x) {
+                const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
+                float v = (T - rp[c1] - rp[c2] + ro[h]) * sgn;
+                if (((bmask >> c1) | (bmask >> c2)) & 1ull) v = 0.0f;
+                ev_p[h] = v;
+                if (WITH_BR) evbr_p[h] = v;
+            }
+            continue;
+        }
+        // ---- showdown: the reach row joins the outstanding table copies; 16-byte chunks, 4-byte tail
+        for (int i = threadIdx.x; i < R / 4; i += blockDim.x) cp_async16(ro + 4 * i, ro_g + 4 * i);
+        for (int h = (R & ~3) + threadIdx.x; h < R; h += blockDim.x) cp_async4(ro + h, ro_g + h);
+        for (int i = threadIdx.x; i <= R; i += blockDim.x) srt[i] = 0.0f;
+        cp_async_wait_all();
+        __syncthreads();
+        // 1. scatter into strength order (pos is a permutation of the live hands: deterministic)
+        for (int h = threadIdx.x; h < R; h += blockDim.x) {
+            const int ps = pos_s[h];
+            if (ps >= 0) srt[ps] = ro[h];
+        }
+        // 2a. centred prefix sums of every card row (reads ro[] only: no barrier needed after the scatter yet)
+        for (int base = 0; base < n_deck; base += blockDim.x >> 2) {
+            const int cc = base + (threadIdx.x >> 2);
+            const bool live = cc < n_deck;
+            float inc[kSegMax];
+            float run = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kSegMax; ++i) {
+                const int idx = qj * seg + i;
+                float v = 0.0f;
+                if (live && i < seg && idx < row_len) {
+                    const int hh = roword_s[cc * row_len + idx];
+                    if (hh >= 0) v = ro[hh];
+                }
+                run += v;
+                inc[i] = run;
+            }
+            float sc = run;  // inclusive scan over the quad
+            float t = __shfl_up_sync(0xffffffffu, sc, 1, 4);
+            if (qj >= 1) sc += t;
+            t = __shfl_up_sync(0xffffffffu, sc, 2, 4);
+            if (qj >= 2) sc += t;
+            const float half = 0.5f * __shfl_sync(0xffffffffu, sc, 3, 4);
+            const float off = (sc - run) - half;
+            if (live) {
+                float* row = rp + cc * kRowStride;
+                if (qj == 0) row[0] = -half;
+#pragma unroll
+                for (int i = 0; i < kSegMax; ++i) {
+                    const int idx = qj * seg + i;
+                    if (i < seg && idx < row_len) row[idx + 1] = off + inc[i];
+                }
+            }
+        }
+        __syncthreads();  // srt[] scattered
+        // 2b. centred exclusive prefix sums over srt[0..R]
+        const int per = (R + 1 + blockDim.x - 1) / blockDim.x;
+        const int i0 = threadIdx.x * per, i1 = min(R + 1, i0 + per);
+        float loc = 0.0f;
+        for (int i = i0; i < i1; ++i) loc += srt[i];
+        float incw = loc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incw, o);
+            if (lane >= o) incw += t;
+        }
+        if (lane == 31) wsum[warp] = incw;
+        __syncthreads();
+        float before = 0.0f, total = 0.0f;
+        for (int k = 0; k < n_warps; ++k) {
+            const float x = wsum[k];
+            if (k < warp) before += x;
+            total += x;
+        }
+        float run = (incw - loc) + before - 0.5f * total;
+        for (int i = i0; i < i1; ++i) {
+            const float x = srt[i];
+            srt[i] = run;
+            run += x;
+        }
+        __syncthreads();
+        // 3. per hand
+        for (int h = threadIdx.x; h < R; h += blockDim.x) {
+            const uint4 q = rec_s[h];
+            const int gs = (int)(short)(q.x & 0xffffu);
+            float v = 0.0f;
+            if (gs >= 0) {
+                const float all = srt[gs] + srt[q.x >> 16];
+                const float rows = (rp[q.y & 0xffffu] + rp[q.y >> 16]) + (rp[q.z & 0xffffu] + rp[q.z >> 16]);
+                v = (all - rows) * scale;
+            }
+            ev_p[h] = v;
+            if (WITH_BR) evbr_p[h] = v;
+        }
+    }
+}
+
 // ---- strength-order tables of complete boards: gs = # live hands strictly weaker, ge = # live hands weaker or equal,
 //      pos = unique position in strength order (ties by hand index); -1 for hands blocked by the board
 __global__ void __launch_bounds__(256) board_order_kernel(const int32_t* __restrict__ ranks, int n_boards, int R,
@@ -992,12 +1047,18 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
     if (!smem_set) {
         cudaFuncSetAttribute(terminal2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        cudaFuncSetAttribute(terminal2_kernel_v1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        cudaFuncSetAttribute(terminal2_kernel_v1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         smem_set = true;
     }
-    const char* v1_env = getenv("PRL_TERMINAL_V1");  // A/B switch, read per call
-    const bool use_v1 = v1_env && v1_env[0] == '1';
+    const char* v_env = getenv("PRL_TERMINAL_V");  // A/B switch, read per call: 2 or 3 (default: newest usable)
+    int term_v = (v_env && v_env[0] == '2') ? 2 : 3;
+    if (term_v == 3 && (!T.work_rec2 || !T.board_hand_rec || (T.n_range & 1))) term_v = 2;
+    const TermSmem tl(T.n_range, T.n_deck);
+    static size_t smem3_max = 0;
+    if (tl.total > smem3_max) {
+        cudaFuncSetAttribute(terminal2_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+        cudaFuncSetAttribute(terminal2_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+        smem3_max = tl.total;
+    }
     int arr_mask = 0;
     for (int p = 0; p < 2; ++p)
         if (c.mask & (1 << p)) arr_mask |= (1 << (2 * p)) | (with_br ? (2 << (2 * p)) : 0);
@@ -1008,9 +1069,9 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
         if (n_term > 0 && chance_phase != 2) {
             c.lo = lo + n_nonterm;
             c.n = n_term;
-            if (use_v1) {
-                if (with_br) terminal2_kernel_v1<true><<<n_term, kTermThreads, tsm, s>>>(c);
-                else terminal2_kernel_v1<false><<<n_term, kTermThreads, tsm, s>>>(c);
+            if (term_v == 3) {
+                if (with_br) terminal2_kernel_v3<true><<<n_term, kTermThreads, tl.total, s>>>(c);
+                else terminal2_kernel_v3<false><<<n_term, kTermThreads, tl.total, s>>>(c);
             } else {
                 if (with_br) terminal2_kernel<true><<<n_term, kTermThreads, tsm, s>>>(c);
                 else terminal2_kernel<false><<<n_term, kTermThreads, tsm, s>>>(c);

@@ -28,7 +28,8 @@ def _stream():
 def structure_records(ft, order):
     """16-byte structure records of the two-card sweeps (prl_tree_t.node_rec2 / work_rec2), host side.
     node record  n: {parent, slot, first slot of the parent's children, kind(parent) | n_children(parent) << 8}
-    work record  t: {node = order[t], its first child, first slot of its children, kind | n_children << 8}"""
+    work record  t: {node = order[t], its first child, first slot of its children, kind | n_children << 8};
+                    terminal entries: {node, board id, pot as float bits, kind | (acted_last & 0xff) << 8}"""
     par = ft.parent.astype(np.int64)
     has_par = par >= 0
     sp_ = np.where(has_par, par, 0)
@@ -46,6 +47,10 @@ def structure_records(ft, order):
     wrec[:, 1] = np.where(nonterm, fc, 0)
     wrec[:, 2] = np.where(nonterm, ft.slot[np.maximum(fc, 0)], 0)
     wrec[:, 3] = ft.kind[order].astype(np.int64) | (ft.n_children[order].astype(np.int64) << 8)
+    term = ~nonterm  # terminal entries: {node, board id, pot (float bits), kind | (acted_last & 0xff) << 8}
+    wrec[term, 1] = ft.board[order[term]]
+    wrec[term, 2] = ft.pot[order[term]].astype(np.float32).view(np.int32)
+    wrec[term, 3] = ft.kind[order[term]].astype(np.int64) | ((ft.acted_last[order[term]].astype(np.int64) & 0xff) << 8)
     return nrec, wrec
 
 

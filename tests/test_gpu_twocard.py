@@ -157,3 +157,26 @@ def test_fused_board_sweep_matches_level_sweeps():
         assert abs(ea - eb) <= 5e-5 * abs(ea), (t, ea, eb)
         ea, eb = a.exploitability_average(), b.exploitability_average()
         assert abs(ea - eb) <= 5e-5 * abs(ea), (t, ea, eb)
+
+
+@pytest.mark.parametrize("algo", ["CFRPlus", "LinearCFR"])
+def test_kernel_variants_agree(algo, monkeypatch):
+    """The record-free fallbacks of the C ABI (NULL node_rec2 / work_rec2 / board_hand_rec: tiled row kernels with
+    pointer chains, table-reading terminal kernel) and both terminal kernel generations follow the same trajectory."""
+    from pokerrl_b200.solver import CFRSolver
+    ft = fhp_tree(random_board_spec(6, 11))
+    ref = None
+    for env in ({}, {"PRL_TERMINAL_V": "2"}, {"PRL_NO_NODE_REC": "1", "PRL_NO_HAND_REC": "1"}):
+        for k in ("PRL_TERMINAL_V", "PRL_NO_NODE_REC", "PRL_NO_HAND_REC"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s = CFRSolver(ft, algo)
+        assert (s.dtree.desc.node_rec2 is None) == ("PRL_NO_NODE_REC" in env)
+        s.iteration(3)
+        got = (s.bufs.regret.cpu().numpy().astype(np.float64), s.exploitability_current(), s.exploitability_average())
+        if ref is None:
+            ref = got
+        else:
+            _close("regret %s" % env, got[0], ref[0], tol=1e-5)
+            assert abs(got[1] - ref[1]) <= 1e-5 * abs(ref[1]) and abs(got[2] - ref[2]) <= 1e-5 * abs(ref[2]), (env, got[1:], ref[1:])

@@ -65,6 +65,10 @@ def test_structure_records_restate_the_pointer_chains():
             assert nrec[n, 3] & 0xff == ft.kind[p] and nrec[n, 3] >> 8 == ft.n_children[p]
     for t in range(ft.n_nodes):
         n = int(order[t])
-        assert wrec[t, 0] == n and wrec[t, 3] & 0xff == ft.kind[n] and wrec[t, 3] >> 8 == ft.n_children[n]
+        assert wrec[t, 0] == n and wrec[t, 3] & 0xff == ft.kind[n]
         if ft.n_children[n] > 0:
+            assert wrec[t, 3] >> 8 == ft.n_children[n]
             assert wrec[t, 1] == ft.first_child[n] and wrec[t, 2] == ft.slot[ft.first_child[n]]
+        else:  # terminal entries carry what terminal2_kernel_v3 needs
+            assert wrec[t, 1] == ft.board[n] and wrec[t, 3] >> 8 == (int(ft.acted_last[n]) & 0xff)
+            assert wrec[t, 2:3].view(np.float32)[0] == np.float32(ft.pot[n])
