@@ -1,5 +1,5 @@
 """A/B of the two-card sweep kernel variants on one GPU (Flop5Holdem, first N board classes).
-usage: python tools/ab_twocard.py [n_boards=20000] [iterations=6]
+usage: python tools/ab_twocard.py [n_boards=20000] [iterations=6] [records-only]
 Variants are selected by the switches the library / solver read: PRL_TERMINAL_V (terminal kernel generation 2 / 3), PRL_NO_HAND_REC
 (no packed per-hand record), PRL_NO_NODE_REC (old tiled row kernels with pointer chains).  For every variant: mean value-
 sweep and reach-sweep time per seat over the timed iterations, and max |regret| / exploitability differences against
@@ -34,6 +34,8 @@ VARIANTS = [
     ("v2 terminal + records", dict(PRL_TERMINAL_V="2", PRL_NO_HAND_REC="0", PRL_NO_NODE_REC="0")),
     ("v3 terminal + records", dict(PRL_TERMINAL_V="3", PRL_NO_HAND_REC="0", PRL_NO_NODE_REC="0")),
 ]
+if len(sys.argv) > 3 and sys.argv[3] == "records-only":
+    VARIANTS = VARIANTS[1:]
 base = None
 for name, env in VARIANTS:
     os.environ.update(env)
