@@ -349,6 +349,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG set on the box) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = "cuda:%d" % local_rank
     t0 = time.perf_counter()
@@ -463,15 +465,16 @@ def main():
             s.iter_counter += 1
         vm, rm = statistics.mean(v_ms), statistics.mean(r_ms)
         achieved = vb / (vm * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "value/regret sweep of one seat = terminal2_kernel + value2_kernel<false,true> + "
+        roofline = {"bound": "hbm", "kernel": "value/regret sweep of one seat = terminal2_kernel_v3 + value2_kernel_v2<false,true> + "
                     "chance_*_kernel over all %d levels (terminal2_kernel is the largest share, see profiles/)" % st["levels"],
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": psrc,
                     "algorithmic_bytes_per_sweep": vb, "sweep_ms": vm, "traffic": None,
                     "traffic_note": "no full-game ncu --set full capture (110 GB resident; replay save/restore); the 20 000-"
-                    "board capture in profiles/r01_c_fhp_kernels.md has terminal2_kernel at 22.2 KB DRAM per terminal row "
-                    "(algorithmic 10.6 KB rows + per-board tables that mostly hit L2), value2_kernel 5.1 KB and "
-                    "reach2_kernel<true> 7.8 KB per node: no re-read excess over the algorithmic bytes",
-                    "reach_sweep": {"kernel": "reach2_kernel<true> x %d levels" % st["levels"], "algorithmic_bytes": rb,
+                    "board capture in profiles/r01_g_twocard_v2.md has terminal2_kernel at 25.1 KB DRAM per terminal row "
+                    "(10.6 KB of rows + the board's tables, shared by neighbouring rows through L2) and reach2_kernel_v2 "
+                    "at 22.9 KB per node on the widest level (3 rows in, 2 rows out = 26.5 KB algorithmic; part of a "
+                    "20 000-board level still sits in L2)",
+                    "reach_sweep": {"kernel": "reach2_kernel_v2<true> x %d levels" % st["levels"], "algorithmic_bytes": rb,
                                     "sweep_ms": rm, "achieved": rb / (rm * 1e-3) / 1e9, "frac": rb / (rm * 1e-3) / 1e9 / peak}}
     else:
         it_ms = []
