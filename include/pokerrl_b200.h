@@ -104,7 +104,10 @@ typedef struct {
                                     kind(parent) | n_children(parent) << 8} - the top-down sweep reads a node's structure
                                     with one 16-byte load; NULL: parent / slot / first_child / n_children / kind are read */
     const void* work_rec2;       /* DEVICE int32[n_nodes][4] or NULL, indexed like `order`: {node, first child, first slot of
-                                    the children, kind | n_children << 8} for the bottom-up sweep over decision nodes */
+                                    the children, kind | n_children << 8} for the bottom-up sweep over decision nodes;
+                                    terminal entries: {node, board id, pot as float bits, kind | (acted_last & 0xff) << 8} */
+    const int64_t* level_nfold;  /* HOST int64[n_levels] or NULL: fold terminals per level (they come first among the
+                                    terminals in `order`); lets fold and showdown rows be launched as separate kernels */
 } prl_tree_t;
 
 /* Caller-owned work buffers. */

@@ -29,7 +29,7 @@ class PrlTree(C.Structure):
         ("board_mult", C.c_void_p), ("board_gs", C.c_void_p), ("board_ge", C.c_void_p), ("board_pos", C.c_void_p),
         ("board_row_order", C.c_void_p), ("board_row_pos", C.c_void_p), ("board_complete", C.c_void_p),
         ("n_sym", C.c_int32), ("sym_perm", C.c_void_p), ("eq_const", C.c_float), ("board_hand_rec", C.c_void_p),
-        ("node_rec2", C.c_void_p), ("work_rec2", C.c_void_p),
+        ("node_rec2", C.c_void_p), ("work_rec2", C.c_void_p), ("level_nfold", C.c_void_p),
     ]
 
 

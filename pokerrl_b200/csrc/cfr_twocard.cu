@@ -745,7 +745,8 @@ struct TermSmem {
 };
 
 // work_rec2 entry of a TERMINAL work-list entry: {node, board id, pot (float bits), kind | (acted_last & 0xff) << 8}
-template <bool WITH_BR>
+// SEG: card-row entries per quad lane held in registers - kSegMax (any deck) or the exact ceil((n_deck - 1) / 4)
+template <bool WITH_BR, int SEG>
 __global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v3(const Ctx2 c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck;
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v3(const Ctx2 c
     const float scale = c.T.eq_const * __int_as_float(w.z) * 0.5f;
     const bool fold = kind == PRL_KIND_FOLD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    const int row_len = n_deck - 1, seg = (row_len + 3) >> 2;
+    const int row_len = n_deck - 1, seg = (SEG == kSegMax) ? (row_len + 3) >> 2 : SEG;
     const int qj = threadIdx.x & 3;
     if (!fold) {  // the board's tables do not depend on the seat: requested once, consumed after the first wait
         const uint4* rec_g = reinterpret_cast<const uint4*>(c.T.board_hand_rec) + (size_t)b * R;
@@ -830,10 +831,10 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v3(const Ctx2 c
         for (int base = 0; base < n_deck; base += blockDim.x >> 2) {
             const int cc = base + (threadIdx.x >> 2);
             const bool live = cc < n_deck;
-            float inc[kSegMax];
+            float inc[SEG];
             float run = 0.0f;
 #pragma unroll
-            for (int i = 0; i < kSegMax; ++i) {
+            for (int i = 0; i < SEG; ++i) {
                 const int idx = qj * seg + i;
                 float v = 0.0f;
                 if (live && i < seg && idx < row_len) {
@@ -854,7 +855,7 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v3(const Ctx2 c
                 float* row = rp + cc * kRowStride;
                 if (qj == 0) row[0] = -half;
 #pragma unroll
-                for (int i = 0; i < kSegMax; ++i) {
+                for (int i = 0; i < SEG; ++i) {
                     const int idx = qj * seg + i;
                     if (i < seg && idx < row_len) row[idx + 1] = off + inc[i];
                 }
@@ -896,6 +897,68 @@ __global__ void __launch_bounds__(kTermThreads) terminal2_kernel_v3(const Ctx2 c
                 const float rows = (rp[q.y & 0xffffu] + rp[q.y >> 16]) + (rp[q.z & 0xffffu] + rp[q.z >> 16]);
                 v = (all - rows) * scale;
             }
+            ev_p[h] = v;
+            if (WITH_BR) evbr_p[h] = v;
+        }
+    }
+}
+
+// Fold rows on their own (generation 4): no board tables, 7 KB of shared memory.  The per-card sums use the
+// lexicographic layout of the range itself - hands (c, x > c) are the contiguous segment ro[base(c) ..], hands (r < c, c)
+// sit at ro[base(r) + c - r - 1] - instead of index arithmetic per element: thread (card c, quarter j) adds every fourth
+// term of both parts in a fixed order, four partials per card are combined in a fixed order.
+constexpr int kFoldThreads = 256;  // 64 card slots x 4 quarters
+inline size_t fold_smem(const prl_tree_t& T) { return sizeof(float) * ((size_t)((T.n_range + 3) & ~3) + 256 + 64 + 32 + 64); }
+
+template <bool WITH_BR>
+__global__ void __launch_bounds__(kFoldThreads) fold2_kernel(const Ctx2 c) {
+    extern __shared__ float fsm[];
+    const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck;
+    float* ro = fsm;                       // [R]  opponent reach row
+    float* part = ro + ((R + 3) & ~3);     // [4][64] partial per-card sums
+    float* cs = part + 256;                // [64] per-card sums; +inf for cards on the board
+    float* red = cs + 64;                  // [32]
+    int* base_s = reinterpret_cast<int*>(red + 32);  // [64] first range index of the hands (c, x > c)
+    const int4 w = reinterpret_cast<const int4*>(c.T.work_rec2)[c.lo + blockIdx.x];
+    const int n = w.x, b = w.y, acted_last = (w.w >> 8) & 0xff;
+    const size_t N = (size_t)c.T.n_nodes;
+    const float scale = c.T.eq_const * __int_as_float(w.z) * 0.5f;
+    const unsigned long long bmask = (b >= 0) ? c.T.board_mask[b] : 0ull;
+    const int cc = threadIdx.x & 63, j = threadIdx.x >> 6;
+    if (threadIdx.x < 64) base_s[threadIdx.x] = threadIdx.x * (2 * n_deck - 1 - threadIdx.x) / 2;
+    const unsigned short* hc = reinterpret_cast<const unsigned short*>(c.T.hand_cards);
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        if (!(c.mask & (1 << p))) continue;
+        const float* ro_g = c.B.reach + ((size_t)(1 - p) * N + n) * ld;
+        float* ev_p = c.B.ev + ((size_t)p * N + n) * ld;
+        float* evbr_p = WITH_BR ? c.B.ev_br + ((size_t)p * N + n) * ld : nullptr;
+        __syncthreads();  // shared arrays are reused by the second seat
+        float psum = 0.0f;
+        for (int h = threadIdx.x; h < R; h += blockDim.x) {
+            const float r = ro_g[h];
+            ro[h] = r;
+            psum += r;
+        }
+        const float T = block_sum(psum, red);  // includes the barriers that publish ro[] and base_s[]
+        float acc = 0.0f;
+        if (cc < n_deck) {
+            for (int r = j; r < cc; r += 4) acc += ro[base_s[r] + cc - r - 1];          // hands (r, cc), r < cc
+            const int b0 = base_s[cc];
+            for (int k = j; k < n_deck - 1 - cc; k += 4) acc += ro[b0 + k];             // hands (cc, cc + 1 + k)
+        }
+        part[j * 64 + cc] = acc;
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const float v = (part[threadIdx.x] + part[64 + threadIdx.x]) + (part[128 + threadIdx.x] + part[192 + threadIdx.x]);
+            cs[threadIdx.x] = ((bmask >> threadIdx.x) & 1ull) ? __int_as_float(0x7f800000) : v;
+        }
+        __syncthreads();
+        const float sgn = (acted_last == p) ? -scale : scale;
+        for (int h = threadIdx.x; h < R; h += blockDim.x) {
+            const unsigned cards = hc[h];  // {c1, c2} as two bytes
+            const float e = T - cs[cards & 0xffu] - cs[cards >> 8] + ro[h];  // -inf for a hand holding a board card
+            const float v = (e > -3.0e38f) ? e * sgn : 0.0f;
             ev_p[h] = v;
             if (WITH_BR) evbr_p[h] = v;
         }
@@ -1049,14 +1112,17 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
         cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         smem_set = true;
     }
-    const char* v_env = getenv("PRL_TERMINAL_V");  // A/B switch, read per call: 2 or 3 (default: newest usable)
-    int term_v = (v_env && v_env[0] == '2') ? 2 : 3;
-    if (term_v == 3 && (!T.work_rec2 || !T.board_hand_rec || (T.n_range & 1))) term_v = 2;
+    const char* v_env = getenv("PRL_TERMINAL_V");  // A/B switch, read per call: 2, 3 or 4
+    int term_v = (v_env && v_env[0] >= '2' && v_env[0] <= '4') ? v_env[0] - '0' : 3;
+    if (term_v >= 3 && (!T.work_rec2 || !T.board_hand_rec || (T.n_range & 1))) term_v = 2;
+    if (term_v == 4 && (!T.level_nfold || T.n_deck > 64 || ((T.n_deck - 1 + 3) >> 2) != 13)) term_v = 3;
     const TermSmem tl(T.n_range, T.n_deck);
     static size_t smem3_max = 0;
     if (tl.total > smem3_max) {
-        cudaFuncSetAttribute(terminal2_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
-        cudaFuncSetAttribute(terminal2_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+        cudaFuncSetAttribute(terminal2_kernel_v3<true, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+        cudaFuncSetAttribute(terminal2_kernel_v3<false, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+        cudaFuncSetAttribute(terminal2_kernel_v3<true, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+        cudaFuncSetAttribute(terminal2_kernel_v3<false, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
         smem3_max = tl.total;
     }
     int arr_mask = 0;
@@ -1069,14 +1135,30 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
         if (n_term > 0 && chance_phase != 2) {
             c.lo = lo + n_nonterm;
             c.n = n_term;
-            if (term_v == 3) {
-                if (with_br) terminal2_kernel_v3<true><<<n_term, kTermThreads, tl.total, s>>>(c);
-                else terminal2_kernel_v3<false><<<n_term, kTermThreads, tl.total, s>>>(c);
+            if (term_v == 4) {  // fold rows (first among the terminals of a level) and showdown rows launched apart
+                const int n_fold = (int)T.level_nfold[d];
+                if (n_fold > 0) {
+                    c.n = n_fold;
+                    if (with_br) fold2_kernel<true><<<n_fold, kFoldThreads, fold_smem(T), s>>>(c);
+                    else fold2_kernel<false><<<n_fold, kFoldThreads, fold_smem(T), s>>>(c);
+                    prl::count_launch();
+                }
+                if (n_term > n_fold) {
+                    c.lo = lo + n_nonterm + n_fold;
+                    c.n = n_term - n_fold;
+                    if (with_br) terminal2_kernel_v3<true, 13><<<c.n, kTermThreads, tl.total, s>>>(c);
+                    else terminal2_kernel_v3<false, 13><<<c.n, kTermThreads, tl.total, s>>>(c);
+                    prl::count_launch();
+                }
+            } else if (term_v == 3) {
+                if (with_br) terminal2_kernel_v3<true, kSegMax><<<n_term, kTermThreads, tl.total, s>>>(c);
+                else terminal2_kernel_v3<false, kSegMax><<<n_term, kTermThreads, tl.total, s>>>(c);
+                prl::count_launch();
             } else {
                 if (with_br) terminal2_kernel<true><<<n_term, kTermThreads, tsm, s>>>(c);
                 else terminal2_kernel<false><<<n_term, kTermThreads, tsm, s>>>(c);
+                prl::count_launch();
             }
-            prl::count_launch();
         }
         if (n_dec > 0 && chance_phase != 2) {
             c.lo = lo;

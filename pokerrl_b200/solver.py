@@ -189,6 +189,10 @@ class DeviceTree:
         if os.environ.get("PRL_NO_NODE_REC", "0") != "1":
             nrec, wrec = structure_records(ft, self.t_order.cpu().numpy())
             self.t_node_rec2, self.t_work_rec2 = up(nrec, np.int32), up(wrec, np.int32)
+        self._level_nfold = np.ascontiguousarray(
+            [int((ft.kind[int(ft.level_start[k]):int(ft.level_start[k + 1])] == nat.KIND_FOLD).sum())
+             for k in range(ft.n_levels)], dtype=np.int64)
+        d.level_nfold = self._level_nfold.ctypes.data
         d.node_rec2 = self.t_node_rec2.data_ptr() if self.t_node_rec2 is not None else None
         d.work_rec2 = self.t_work_rec2.data_ptr() if self.t_work_rec2 is not None else None
         d.n_sym = 0 if sp is None else int(sp.shape[0])

@@ -118,6 +118,23 @@ def fold_kernel_flow(ro):
     return ro.sum() - cs[C1] - cs[C2] + ro
 
 
+def fold2_kernel_flow(ro):
+    """fold2_kernel: thread (card cc, quarter j) adds every fourth hand (r < cc, cc) and every fourth hand (cc, x > cc),
+    addressed through the lexicographic layout of the range; four partials per card"""
+    base = [c * (2 * N_DECK - 1 - c) // 2 for c in range(64)]
+    part = np.zeros((4, 64))
+    for j in range(4):
+        for cc in range(N_DECK):
+            acc = 0.0
+            for r in range(j, cc, 4):
+                acc += ro[base[r] + cc - r - 1]
+            for k in range(j, N_DECK - 1 - cc, 4):
+                acc += ro[base[cc] + k]
+            part[j, cc] = acc
+    cs = (part[0] + part[1]) + (part[2] + part[3])
+    return ro.sum() - cs[C1] - cs[C2] + ro
+
+
 @pytest.mark.parametrize("seed", [0, 1])
 def test_showdown_flow_equals_definition(seed):
     rng = np.random.default_rng(seed)
@@ -144,3 +161,4 @@ def test_fold_flow_equals_definition():
     share = (C1[:, None] == C1[None, :]) | (C1[:, None] == C2[None, :]) | (C2[:, None] == C1[None, :]) | \
             (C2[:, None] == C2[None, :])
     np.testing.assert_allclose(fold_kernel_flow(ro), (~share).astype(float) @ ro, atol=1e-9)
+    np.testing.assert_allclose(fold2_kernel_flow(ro), (~share).astype(float) @ ro, atol=1e-9)

@@ -1,6 +1,6 @@
 """A/B of the two-card sweep kernel variants on one GPU (Flop5Holdem, first N board classes).
 usage: python tools/ab_twocard.py [n_boards=20000] [iterations=6] [records-only]
-Variants are selected by the switches the library / solver read: PRL_TERMINAL_V (terminal kernel generation 2 / 3), PRL_NO_HAND_REC
+Variants are selected by the switches the library / solver read: PRL_TERMINAL_V (terminal kernel generation 2 / 3 / 4), PRL_NO_HAND_REC
 (no packed per-hand record), PRL_NO_NODE_REC (old tiled row kernels with pointer chains).  For every variant: mean value-
 sweep and reach-sweep time per seat over the timed iterations, and max |regret| / exploitability differences against
 the first (baseline) variant after the same number of iterations."""
@@ -33,9 +33,12 @@ VARIANTS = [
     ("no records (fallbacks)", dict(PRL_TERMINAL_V="2", PRL_NO_HAND_REC="1", PRL_NO_NODE_REC="1")),
     ("v2 terminal + records", dict(PRL_TERMINAL_V="2", PRL_NO_HAND_REC="0", PRL_NO_NODE_REC="0")),
     ("v3 terminal + records", dict(PRL_TERMINAL_V="3", PRL_NO_HAND_REC="0", PRL_NO_NODE_REC="0")),
+    ("v4 fold / showdown apart", dict(PRL_TERMINAL_V="4", PRL_NO_HAND_REC="0", PRL_NO_NODE_REC="0")),
 ]
 if len(sys.argv) > 3 and sys.argv[3] == "records-only":
     VARIANTS = VARIANTS[1:]
+if len(sys.argv) > 3 and sys.argv[3] == "newest":
+    VARIANTS = VARIANTS[2:]
 base = None
 for name, env in VARIANTS:
     os.environ.update(env)
