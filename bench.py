@@ -465,7 +465,7 @@ def main():
             s.iter_counter += 1
         vm, rm = statistics.mean(v_ms), statistics.mean(r_ms)
         achieved = vb / (vm * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "value/regret sweep of one seat = terminal2_kernel_v3 + value2_kernel_v2<false,true> + "
+        roofline = {"bound": "hbm", "kernel": "value/regret sweep of one seat = fold2_kernel + terminal2_kernel_v3 + value2_kernel_v2<false,true> + "
                     "chance_*_kernel over all %d levels (terminal2_kernel is the largest share, see profiles/)" % st["levels"],
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": psrc,
                     "algorithmic_bytes_per_sweep": vb, "sweep_ms": vm, "traffic": None,

@@ -1112,8 +1112,8 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
         cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         smem_set = true;
     }
-    const char* v_env = getenv("PRL_TERMINAL_V");  // A/B switch, read per call: 2, 3 or 4
-    int term_v = (v_env && v_env[0] >= '2' && v_env[0] <= '4') ? v_env[0] - '0' : 3;
+    const char* v_env = getenv("PRL_TERMINAL_V");  // A/B switch, read per call: 2, 3 or 4 (default: newest usable)
+    int term_v = (v_env && v_env[0] >= '2' && v_env[0] <= '4') ? v_env[0] - '0' : 4;
     if (term_v >= 3 && (!T.work_rec2 || !T.board_hand_rec || (T.n_range & 1))) term_v = 2;
     if (term_v == 4 && (!T.level_nfold || T.n_deck > 64 || ((T.n_deck - 1 + 3) >> 2) != 13)) term_v = 3;
     const TermSmem tl(T.n_range, T.n_deck);

@@ -162,11 +162,12 @@ def test_fused_board_sweep_matches_level_sweeps():
 @pytest.mark.parametrize("algo", ["CFRPlus", "LinearCFR"])
 def test_kernel_variants_agree(algo, monkeypatch):
     """The record-free fallbacks of the C ABI (NULL node_rec2 / work_rec2 / board_hand_rec: tiled row kernels with
-    pointer chains, table-reading terminal kernel) and both terminal kernel generations follow the same trajectory."""
+    pointer chains, table-reading terminal kernel) and the terminal kernel generations (default 4: fold rows apart; 3: one
+    kernel, cp.async staging; 2: direct loads) follow the same trajectory."""
     from pokerrl_b200.solver import CFRSolver
     ft = fhp_tree(random_board_spec(6, 11))
     ref = None
-    for env in ({}, {"PRL_TERMINAL_V": "2"}, {"PRL_NO_NODE_REC": "1", "PRL_NO_HAND_REC": "1"}):
+    for env in ({}, {"PRL_TERMINAL_V": "3"}, {"PRL_TERMINAL_V": "2"}, {"PRL_NO_NODE_REC": "1", "PRL_NO_HAND_REC": "1"}):
         for k in ("PRL_TERMINAL_V", "PRL_NO_NODE_REC", "PRL_NO_HAND_REC"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
