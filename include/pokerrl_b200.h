@@ -25,6 +25,10 @@ extern "C" {
 
 typedef void* prl_stream_t; /* cudaStream_t */
 
+/* bumped whenever a struct below changes; prl_abi_version() returns the value the library was built with
+   (2: prl_tree_t gained board_hand_rec / node_rec2 / work_rec2 / level_nfold) */
+#define PRL_ABI_VERSION 2
+
 /* node kinds (game/_/tree/_/nodes.py:8-62 + ValueFiller.py:34-62) */
 enum {
     PRL_KIND_P0 = 0,             /* player 0 acts next */

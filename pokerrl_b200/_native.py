@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpokerrl_b200.so")
 # enums of include/pokerrl_b200.h
 KIND_P0, KIND_P1, KIND_CHANCE, KIND_FOLD, KIND_SHOWDOWN, KIND_SHOWDOWN_ALLIN = range(6)
 ALGO_VANILLA, ALGO_CFR_PLUS, ALGO_LINEAR = 0, 1, 2
+ABI_VERSION = 2  # include/pokerrl_b200.h: PRL_ABI_VERSION
 STRAT_F32, STRAT_UNIFORM64, STRAT_AVG_F64, STRAT_AVG_SUM, STRAT_AVG_F32 = range(5)
 
 
@@ -74,6 +75,9 @@ def lib():
             "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
     L = C.CDLL(LIB_PATH)
     L.prl_abi_version.restype = C.c_int
+    if L.prl_abi_version() != ABI_VERSION:
+        raise RuntimeError("pokerrl_b200: %s was built for ABI %d, the Python side expects %d - rebuild it with "
+                           "`python -m pokerrl_b200.csrc.build`" % (LIB_PATH, L.prl_abi_version(), ABI_VERSION))
     L.prl_last_error.restype = C.c_char_p
     tp, bp, ip = C.POINTER(PrlTree), C.POINTER(PrlBuffers), C.POINTER(C.c_int)
     L.prl_reach_pass.argtypes = [tp, bp, C.c_int, ip, C.c_void_p]

@@ -24,6 +24,6 @@ int check(cudaError_t e, const char* where) {
 void count_launch() { ++g_launches; }
 }  // namespace prl
 
-extern "C" int prl_abi_version(void) { return 1; }
+extern "C" int prl_abi_version(void) { return PRL_ABI_VERSION; }
 extern "C" const char* prl_last_error(void) { return g_err; }
 extern "C" unsigned long long prl_launch_count(void) { return g_launches; }

@@ -67,4 +67,29 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert len(names) >= 15
     for n in sorted(set(names)):
         assert hasattr(L, n), n
-    assert L.prl_abi_version() >= 1
+    assert L.prl_abi_version() == _native.ABI_VERSION
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct in include/pokerrl_b200.h, as gcc lays them out, against the ctypes mirrors
+    in pokerrl_b200/_native.py (a silent mismatch would shift every pointer the kernels read)"""
+    import ctypes as C
+    import subprocess
+    from pokerrl_b200 import _native
+    pairs = [("prl_tree_t", _native.PrlTree), ("prl_buffers_t", _native.PrlBuffers), ("prl_subtree_t", _native.PrlSubtree),
+             ("prl_env_cfg_t", _native.PrlEnvCfg)]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "pokerrl_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src.append('printf("abi %d\\n", PRL_ABI_VERSION); return 0; }')
+    c_file, exe = tmp_path / "layout.c", tmp_path / "layout"
+    c_file.write_text("\n".join(src))
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(c_file), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(got["abi"]) == _native.ABI_VERSION
+    for cname, cls in pairs:
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
