@@ -7,10 +7,13 @@ children, parent, p_id_acting_next, p_id_acted_last, action, allowed_actions, is
 reach_probs / ev / ev_br [2,R], exploitability [2], env_state (public part).  Host copies are fetched lazily after
 each pass.
 """
+import os
+
 import numpy as np
 import torch
 
 from pokerrl_b200 import _native as nat
+from pokerrl_b200.game import tree_export
 from pokerrl_b200.game.Poker import Poker
 from pokerrl_b200.game.flat_tree import (FlatTree, KIND_CHANCE, KIND_FOLD, KIND_P1)
 from pokerrl_b200.solver import DeviceTree, TreeBuffers, TreeOps
@@ -149,7 +152,11 @@ class PublicTree:
         self._stop_at_street_arg = stop_at_street
         self._put_out_new_round_after_limit = put_out_new_round_after_limit
         self._device = device
-        self.dir_tree_vis_data = None
+        # optional PokerViz export: only into an installed viewer that carries the reference's marker file
+        # (PublicTree.py:45-56); otherwise export_to_file() does nothing
+        viz = os.path.join("C:\\" if os.name == "nt" else os.path.expanduser("~/"), "PokerRL_Viz")
+        installed = os.path.isdir(viz) and os.path.isfile(os.path.join(viz, "ALLOWED_TO_WRITE_HERE.dontdelete"))
+        self.dir_tree_vis_data = os.path.join(viz, "data") if installed else None
         self.root = None
         self.flat = None
         self._n_seats = env_bldr.N_SEATS
@@ -184,6 +191,7 @@ class PublicTree:
         self.modes = [nat.STRAT_UNIFORM64, nat.STRAT_UNIFORM64]
         self._cache = {}
         self._root_expl = None
+        self._has_reach = self._has_ev = False
         self.root = NodeView(self, 0)
 
     # ---- strategy filling (StrategyFiller.py:17-46)
@@ -226,11 +234,13 @@ class PublicTree:
 
     def update_reach_probs(self):
         self.ops.reach_pass(self.modes)
+        self._has_reach = True
         self._cache.pop("reach", None)
 
     def compute_ev(self):
         self.ops.value_pass(self.modes, 3, True)
         self._root_expl = self.ops.root_exploitability()
+        self._has_ev = True
         self._cache.pop("ev", None)
         self._cache.pop("ev_br", None)
 
@@ -261,12 +271,13 @@ class PublicTree:
         tab = self.bufs.strat if m == nat.STRAT_F32 else self.bufs.avg
         return tab[fs:fs + A, :ft.R].cpu().numpy().T.copy()
 
-    # ---- export hooks of the reference (PokerViz browser tool; not part of the compute path)
-    def export_to_file(self, name="data"):
-        return None
-
+    # ---- export hooks of the reference (PokerViz browser tool; not part of the compute path): PublicTree.py:143-149
     def get_tree_as_dict(self):
-        def rec(node):
-            return {"action": node.action, "p_id_acting_next": node.p_id_acting_next,
-                    "main_pot": node.env_state["main_pot"], "children": [rec(c) for c in node.children]}
-        return rec(self.root)
+        reach = self._host("reach") if self._has_reach else None
+        ev, ev_br = (self._host("ev"), self._host("ev_br")) if self._has_ev else (None, None)
+        return tree_export.export_tree_dict(self.flat, reach, ev, ev_br, self._node_strategy if self._has_reach else None)
+
+    def export_to_file(self, name="data"):
+        if self.dir_tree_vis_data is not None:
+            os.makedirs(self.dir_tree_vis_data, exist_ok=True)
+            tree_export.write_tree_js(os.path.join(self.dir_tree_vis_data, str(name) + ".js"), self.get_tree_as_dict())
