@@ -277,7 +277,14 @@ def main():
     ap.add_argument("--fhp-boards", type=int, default=0, help="debug: only the first n isomorphism classes")
     ap.add_argument("--hulh-turns", type=int, default=0, help="hulh: only the first n turn cards (memory: the full 49 need >= 2 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--schedule", default=None, choices=["levels", "tasks"],
+                    help="one-card workloads: level-synchronous sweeps (default) or the experimental subtree schedule")
+    ap.add_argument("--task-threshold", type=int, default=None)
     a = ap.parse_args()
+    if a.schedule is not None:
+        os.environ["PRL_SCHEDULE"] = a.schedule
+    if a.task_threshold is not None:
+        os.environ["PRL_TASK_THRESHOLD"] = str(a.task_threshold)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -306,6 +313,8 @@ def main():
         cfg = {"workload": "DiscretizedNLLeduc CFR+ delay 0, bet_sets.%s, stack 20000%s, exact BR (current+average) "
                            "every %d iterations" % (LEDUC[a.workload], " + 1000*rank (one tree per rank)" if world > 1 else "",
                                                     a.eval_every)}
+        if os.environ.get("PRL_SCHEDULE", "levels") == "tasks":
+            cfg["schedule"] = "subtree tasks, threshold %s nodes" % os.environ.get("PRL_TASK_THRESHOLD", "1024")
 
     # ------------------------------------------------------------------ reference arm (CPU restatement)
     if a.impl == "reference":
@@ -489,8 +498,11 @@ def main():
         l_ms = statistics.mean(it_ms)
         bpl = a.eval_every * 2 * (vb + rb)
         achieved = bpl / (l_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "cfr_iterations_kernel<6,2> (persistent cooperative kernel: %d CFR+ iterations "
-                    "= %d level steps with grid barriers per launch)" % (a.eval_every, a.eval_every * 2 * (2 * st["levels"] - 1)),
+        kname = ("cfr_iterations_kernel<6,2> (persistent cooperative kernel: %d CFR+ iterations = %d level steps with grid "
+                 "barriers per launch)" % (a.eval_every, a.eval_every * 2 * (2 * st["levels"] - 1)))
+        if getattr(s, "schedule", "levels") == "tasks":
+            kname = "task_sweep_kernel<6,2> + trunk_sweep_kernel<6,2> (subtree schedule: 4 launches per iteration + 1 per call)"
+        roofline = {"bound": "hbm", "kernel": kname,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": psrc,
                     "algorithmic_bytes_per_launch": bpl, "launch_ms": l_ms, "traffic": None,
                     "note": "latency/occupancy-bound, not HBM-bound: R = 6 rows, 27 dependent level steps per seat"}
