@@ -22,6 +22,7 @@
 //   averaging       cfr/CFRPlus.py:65-87, cfr/LinearCFR.py:53-76, cfr/VanillaCFR.py:54-77
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "pokerrl_b200.h"
@@ -474,8 +475,10 @@ __device__ __forceinline__ void root_exploitability(const prl_tree_t& T, const p
     out[p] = s;
 }
 
-template <int R, int NS>
-__global__ void __launch_bounds__(kPThreads, 1) cfr_iterations_kernel(Ctx c, const Levels lv, const int n_iters) {
+// THREADS: block size = threads per SM (one block per SM).  512 is the measured default (128 registers per thread);
+// 1024 caps the kernel at 64 registers for twice the warps per SM (PRL_PERSISTENT_THREADS=1024, unmeasured so far).
+template <int R, int NS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) cfr_iterations_kernel(Ctx c, const Levels lv, const int n_iters) {
     cg::grid_group grid = cg::this_grid();
     // warp w of block b takes 32-entry chunk (w * gridDim + b) of the kind-sorted work list: consecutive chunks go to
     // different SMs, so every SM sees the same mix of node kinds (no per-kind load imbalance at the grid barrier)
@@ -676,28 +679,35 @@ int make_levels(const prl_tree_t* T, Levels* lv) {
 
 // co-resident grid for a cooperative launch of `kernel` (cached per kernel and device)
 template <typename K>
-int coop_grid(K kernel, int* grid) {
+int coop_grid(K kernel, int* grid, int threads = kPThreads) {
     static int cached[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 64 && cached[dev]) { *grid = cached[dev]; return 0; }
+    if (dev < 64 && cached[dev] && threads == kPThreads) { *grid = cached[dev]; return 0; }
     int per_sm = 0, sms = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return prl::check(e, "cooperative occupancy query");
     if (per_sm < 1) return prl::fail("prl: persistent kernel does not fit on an SM");
     *grid = sms;  // one block per SM
-    if (dev < 64) cached[dev] = *grid;
+    if (dev < 64 && threads == kPThreads) cached[dev] = *grid;
     return 0;
 }
 
 template <int R>
 int launch_iterations(Ctx& c, Levels& lv, int n_iters, cudaStream_t s) {
     int grid = 0;
-    if (int e = coop_grid(cfr_iterations_kernel<R, 2>, &grid)) return e;
     void* args[] = {&c, &lv, &n_iters};
+    const char* wide = getenv("PRL_PERSISTENT_THREADS");  // experiment switch: 1024 threads per SM at 64 registers
+    if (wide && atoi(wide) == 1024) {
+        if (int e = coop_grid(cfr_iterations_kernel<R, 2, 1024>, &grid, 1024)) return e;
+        prl::count_launch();
+        return prl::check(cudaLaunchCooperativeKernel((void*)cfr_iterations_kernel<R, 2, 1024>, dim3(grid), dim3(1024), args, 0, s),
+                          "prl_cfr_iterations");
+    }
+    if (int e = coop_grid(cfr_iterations_kernel<R, 2, kPThreads>, &grid)) return e;
     prl::count_launch();
-    return prl::check(cudaLaunchCooperativeKernel((void*)cfr_iterations_kernel<R, 2>, dim3(grid), dim3(kPThreads), args, 0, s),
+    return prl::check(cudaLaunchCooperativeKernel((void*)cfr_iterations_kernel<R, 2, kPThreads>, dim3(grid), dim3(kPThreads), args, 0, s),
                       "prl_cfr_iterations");
 }
 

@@ -30,3 +30,16 @@ def test_task_schedule_equals_level_schedule(algo, name, threshold):
             assert torch.equal(getattr(a.bufs, k), getattr(b.bufs, k)), (k, a.iter_counter)
         assert a.exploitability_current() == b.exploitability_current()
         assert a.exploitability_average() == b.exploitability_average()
+
+
+def test_wide_persistent_kernel_equals_default(monkeypatch):
+    """PRL_PERSISTENT_THREADS=1024: the persistent iteration kernel at 1024 threads / 64 registers per SM"""
+    from pokerrl_b200.solver import CFRSolver
+    ft = make_flat_tree("NLLeduc_B3")
+    a = CFRSolver(ft, "CFRPlus", avg_f64=True)
+    a.iteration(4)
+    monkeypatch.setenv("PRL_PERSISTENT_THREADS", "1024")
+    b = CFRSolver(ft, "CFRPlus", avg_f64=True)
+    b.iteration(4)
+    for k in ("regret", "strat", "avg", "reach"):
+        assert torch.equal(getattr(a.bufs, k), getattr(b.bufs, k)), k
