@@ -81,3 +81,24 @@ def test_b5_statistics_quoted_in_design_md():
     _, ft = bench.make_tree("leduc_b5", 20000)
     st = TaskSchedule(ft, 1024).stats()
     assert (st["trunk_nodes"], st["tasks"], st["task_size_max"]) == (551, 3037, 1011)
+
+
+@pytest.mark.parametrize("algo", ["CFRPlus", "LinearCFR", "VanillaCFR"])
+@pytest.mark.parametrize("game,threshold", [("NLLeduc_POT", 64), ("NLLeduc_POT", 10 ** 6), ("StandardLeduc", 20),
+                                            ("NLLeduc_POT", 0)])
+def test_task_order_reproduces_level_order_bit_for_bit(algo, game, threshold):
+    """The orchestration of prl_cfr_iterations_tasks restated on the host (oracle/cfr_oracle.c:
+    orc_cfr_iterations_tasks, same launch sequence and pending-sweep bookkeeping as run_task_iterations in
+    pokerrl_b200/csrc/cfr_levels.cu) against the level order, which the reference's fixtures pin."""
+    import cfr_c
+    ft = make_flat_tree(game)
+    a = cfr_c.OracleCSolver(ft, algo, avg_f64=(algo == "CFRPlus"), n_threads=1)
+    b = cfr_c.OracleCSolver(ft, algo, avg_f64=(algo == "CFRPlus"), n_threads=1)
+    b.set_task_schedule(threshold)
+    for n in (1, 1, 3):
+        a.iteration(n)
+        b.iteration(n)
+        for k in ("regret", "strat", "avg", "reach"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (k, a.iter_counter)
+        assert a.exploitability_current() == b.exploitability_current()
+        assert a.exploitability_average() == b.exploitability_average()
