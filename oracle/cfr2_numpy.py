@@ -20,6 +20,21 @@ import numpy as np
 KIND_P0, KIND_P1, KIND_CHANCE, KIND_FOLD, KIND_SHOWDOWN, KIND_SHOWDOWN_ALLIN = 0, 1, 2, 3, 4, 5
 
 
+def fold_row(inc, ro):
+    """ValueFiller.py:103-125 for two-card hands (before K, sign and pot): mass of the opponent hands sharing no card
+    with mine = total - (hands holding my first card) - (hands holding my second card) + (my own hand, subtracted twice).
+    inc = hand-card incidence [R, n_deck]."""
+    cs = inc.T @ ro  # per-card sums
+    return ro.sum() - inc @ cs + (int(inc[0].sum()) - 1) * ro
+
+
+def sign_matrix(ranks, compat, blocked):
+    """ValueFiller.py:140-155 as a matrix: S[h, h'] = sign(rank_h - rank_h') for card-disjoint live hands, else 0"""
+    rk = np.asarray(ranks).astype(np.int64)
+    s = np.sign(rk[:, None] - rk[None, :]).astype(np.float64)
+    return s * (compat & ~blocked[:, None] & ~blocked[None, :])
+
+
 class Oracle2Tree:
     def __init__(self, ft, hand_cards, board_ranks, board_prob, board_mult, sym_perm=None, eq_const=None):
         """ft: FlatTree; hand_cards int[R, n_hole]; board_ranks int32[n_boards_total, R] (global board id order,
@@ -87,10 +102,7 @@ class Oracle2Tree:
 
     def _sign_matrix(self, b):
         if b not in self._sign:
-            rk = self.board_ranks[b].astype(np.int64)
-            s = np.sign(rk[:, None] - rk[None, :]).astype(np.float64)
-            ok = self.compat & ~self.board_blocked[b][:, None] & ~self.board_blocked[b][None, :]
-            self._sign[b] = s * ok
+            self._sign[b] = sign_matrix(self.board_ranks[b], self.compat, self.board_blocked[b])
             if len(self._sign) > 64:
                 self._sign.pop(next(iter(self._sign)))
         return self._sign[b]
@@ -105,9 +117,7 @@ class Oracle2Tree:
                 for p in range(2):
                     ro = self.reach[n, 1 - p]
                     if k == KIND_FOLD:
-                        cs = self.inc.T @ ro  # per-card sums
-                        # opponent hands sharing no card with mine (inclusion-exclusion over my cards)
-                        e = ro.sum() - self.inc @ cs + (self.hand_cards.shape[1] - 1) * ro
+                        e = fold_row(self.inc, ro)  # opponent hands sharing no card with mine
                         eq[p] = -e if ft.acted_last[n] == p else e
                     elif k == KIND_SHOWDOWN:
                         eq[p] = self._sign_matrix(b) @ ro
