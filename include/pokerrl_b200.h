@@ -26,8 +26,8 @@ extern "C" {
 typedef void* prl_stream_t; /* cudaStream_t */
 
 /* bumped whenever a struct below changes; prl_abi_version() returns the value the library was built with
-   (2: prl_tree_t gained board_hand_rec / node_rec2 / work_rec2 / level_nfold) */
-#define PRL_ABI_VERSION 2
+   (2: prl_tree_t gained board_hand_rec / node_rec2 / work_rec2 / level_nfold; 3: board engine, legacy LUT natives) */
+#define PRL_ABI_VERSION 3
 
 /* node kinds (game/_/tree/_/nodes.py:8-62 + ValueFiller.py:34-62) */
 enum {
@@ -245,6 +245,65 @@ int prl_reach_levels(const prl_tree_t* tree, const prl_buffers_t* buf, int playe
  * int16[n_boards][n_deck][n_deck-1], row_pos = DEVICE uint8[n_boards][n_range][4] (see prl_tree_t). */
 int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_range, int n_deck, int16_t* gs, int16_t* ge,
                            int16_t* pos, int16_t* row_order, uint8_t* row_pos, prl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Board-resident CFR+ engine (csrc/cfr_board.cu) for two-card games with ONE chance layer whose post-deal subtree has
+ * the compiled shape (Flop5Holdem, PokerRL/game/games.py:222-254: 15 nodes per board).  Replaces, for the post-deal
+ * levels, ValueFiller.compute_cf_values_heads_up (ValueFiller.py:21-158), StrategyFiller._update_reach_probs
+ * (StrategyFiller.py:118-146) and the regret / matching / averaging of CFRPlus.py:37-87: one persistent kernel walks
+ * (board, seat) units with the subtree in registers / shared memory.  Table rows of a board are stored in the board's
+ * strength order over the n_live = C(n_deck - 5, 2) hands that hold no board card (stride ldb); the strategy is not
+ * stored (regret matching of the regret rows).  The pre-deal trunk stays with the level sweeps above.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t n_boards;  /* boards resident on this device */
+    int32_t n_range;   /* 1326 */
+    int32_t ld;        /* stride of natural-order rows (trunk vectors) */
+    int32_t n_deck;    /* 52 */
+    int32_t n_local;   /* nodes of the post-deal subtree, breadth-first, local 0 = first node after the deal */
+    int32_t frac_bits; /* the chance-node sums are accumulated as int64 fixed point with this many fraction bits */
+    int32_t grid;      /* CTAs of the persistent kernel; 0 = library default (2 per SM) */
+    float eq_const;    /* C(deck,2)/C(deck-2,2) (ValueFiller.py:19 generalised) */
+    int8_t kind[16], parent[16], first_child[16], n_children[16], acted_last[16];
+    float pot[16];
+    int64_t row0[16];  /* table row of local node i (a child of a decision node) on board 0; -1: none */
+    int32_t row_m[16]; /* row(i, j) = row0[i] + j * row_m[i] (= fan-out of the parent) */
+    const void* tables;      /* DEVICE [n_boards][blob bytes] built by prl_board_build_tables */
+    const float* board_prob; /* DEVICE float[n_boards]: deal probability applied to both reach rows */
+    const float* board_mult; /* DEVICE float[n_boards]: weight in the parent's sum (orbit size / 24 or 1) */
+    float* regret;           /* DEVICE float[n_rows][ldb] */
+    float* avg;              /* DEVICE float[n_rows][ldb]  CFR+ average strategy */
+    int64_t* w_private;      /* DEVICE int64[grid][2][n_range] scratch */
+    int64_t* w_total;        /* DEVICE int64[2][n_range]: fixed-point sums over this device's boards of board_mult * root
+                                value (array 0: ev, array 1: ev_br), natural hand order */
+} prl_board_game_t;
+
+/* out[8] = {n_live, ldb, blob bytes per board, byte offset of the int16 hand ids, byte offset of the card rows,
+ *           live cards, padded card-row length, nodes of the compiled shape} */
+int prl_board_layout(int32_t* out);
+int prl_board_grid(void);                              /* default CTA count on the current device */
+int prl_board_shape_ok(const prl_board_game_t* g);     /* 1 iff kind / parent / first_child / n_children match */
+
+/* ranks = DEVICE int32[n_boards][1326] (prl_hand_rank_boards), board_mask = DEVICE uint64[n_boards] -> blob */
+int prl_board_build_tables(const int32_t* ranks, const uint64_t* board_mask, const int8_t* hand_cards, int n_boards,
+                           void* blob, prl_stream_t stream);
+
+/* One sweep over all boards for seat p.  eval == 0: CFR+ update of p's post-deal rows (iteration iter, averaging delay
+ * `delay`); eval != 0: values and best-response values of p with the strategies of p / the opponent taken from
+ * src_own / src_opp (0 = regret matching of `regret`, 1 = rows of `avg`).  trunk_reach_opp = DEVICE float[ld]: reach row
+ * of the opponent at the chance node.  Leaves the fixed-point sums in g->w_total (zeroed first). */
+int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int src_own, int src_opp, const float* trunk_reach_opp,
+                    int iter, int delay, prl_stream_t stream);
+
+/* out[a][h] = 2^-frac_bits * sum over the n_sym suit permutations of w_total[a][perm(h)] (n_sym <= 1: no symmetrisation),
+ * a < n_arr: the chance node's rows for the trunk sweep (after an all-reduce of w_total across GPUs, if sharded). */
+int prl_board_collect(const prl_board_game_t* g, int n_arr, const int16_t* sym_perm, int n_sym, float* out, int ld,
+                      prl_stream_t stream);
+
+/* Strength-ordered rows <-> natural-order rows.  row_src / row_dst = DEVICE int64[rows_per_board][2] {row on board 0,
+ * stride per board} in the strength-ordered table and in a natural-order table of stride ld. */
+int prl_board_permute(const prl_board_game_t* g, int rows_per_board, const int64_t* row_src, const int64_t* row_dst,
+                      float* sorted_tab, float* natural_tab, int ld, int to_natural, prl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * 7-card Hold'em hand evaluation (replaces lib_hand_eval.so; int32 strength, higher = better, identical encoding incl.

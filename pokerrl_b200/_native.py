@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpokerrl_b200.so")
 # enums of include/pokerrl_b200.h
 KIND_P0, KIND_P1, KIND_CHANCE, KIND_FOLD, KIND_SHOWDOWN, KIND_SHOWDOWN_ALLIN = range(6)
 ALGO_VANILLA, ALGO_CFR_PLUS, ALGO_LINEAR = 0, 1, 2
-ABI_VERSION = 2  # include/pokerrl_b200.h: PRL_ABI_VERSION
+ABI_VERSION = 3  # include/pokerrl_b200.h: PRL_ABI_VERSION
 STRAT_F32, STRAT_UNIFORM64, STRAT_AVG_F64, STRAT_AVG_SUM, STRAT_AVG_F32 = range(5)
 
 
@@ -51,6 +51,16 @@ class PrlSubtree(C.Structure):
                 ("node_k", C.c_int32 * 16), ("kind", C.c_int8 * 16), ("parent", C.c_int8 * 16),
                 ("first_child", C.c_int8 * 16), ("n_children", C.c_int8 * 16), ("acted_last", C.c_int8 * 16),
                 ("pot", C.c_float * 16)]
+
+
+class PrlBoardGame(C.Structure):
+    _fields_ = [("n_boards", C.c_int32), ("n_range", C.c_int32), ("ld", C.c_int32), ("n_deck", C.c_int32),
+                ("n_local", C.c_int32), ("frac_bits", C.c_int32), ("grid", C.c_int32), ("eq_const", C.c_float),
+                ("kind", C.c_int8 * 16), ("parent", C.c_int8 * 16), ("first_child", C.c_int8 * 16),
+                ("n_children", C.c_int8 * 16), ("acted_last", C.c_int8 * 16), ("pot", C.c_float * 16),
+                ("row0", C.c_int64 * 16), ("row_m", C.c_int32 * 16),
+                ("tables", C.c_void_p), ("board_prob", C.c_void_p), ("board_mult", C.c_void_p), ("regret", C.c_void_p),
+                ("avg", C.c_void_p), ("w_private", C.c_void_p), ("w_total", C.c_void_p)]
 
 
 class PrlEnvCfg(C.Structure):
@@ -113,6 +123,18 @@ def lib():
     L.prl_hand_rank_boards.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.prl_hand_rank_7.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     for f in ("prl_hand_rank_boards", "prl_hand_rank_7"):
+        getattr(L, f).restype = C.c_int
+    gp = C.POINTER(PrlBoardGame)
+    L.prl_board_layout.argtypes = [C.POINTER(C.c_int32)]
+    L.prl_board_grid.argtypes = []
+    L.prl_board_shape_ok.argtypes = [gp]
+    L.prl_board_build_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.prl_board_sweep.argtypes = [gp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.prl_board_collect.argtypes = [gp, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.prl_board_permute.argtypes = [gp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p]
+    for f in ("prl_board_layout", "prl_board_grid", "prl_board_shape_ok", "prl_board_build_tables", "prl_board_sweep",
+              "prl_board_collect", "prl_board_permute"):
         getattr(L, f).restype = C.c_int
     ep = C.POINTER(PrlEnvCfg)
     L.prl_env_state_fields.restype = C.c_int

@@ -35,8 +35,9 @@ class CFRBase:
         env_cls = get_env_cls_from_str(self._game_cls_str)
         self._env_bldrs = [HistoryEnvBuilder(env_cls=env_cls, env_args=a) for a in self._env_args]
         self._solvers = [self._make_solver(env_cls, a, delay, device, avg_f64, board_spec) for a in self._env_args]
-        self._flat_trees = [s.ft for s in self._solvers]
-        for ft, a in zip(self._flat_trees, self._env_args):
+        self._flat_trees = [getattr(s, "ft", None) for s in self._solvers]  # None: board engine (no node arrays)
+        for s, a in zip(self._solvers, self._env_args):
+            ft = getattr(s, "ft", None) or s
             print("Tree with stack size", a.starting_stack_sizes_list, "has", ft.n_nodes - 1,
                   "nodes out of which", ft.n_nonterm - 1, "are non-terminal.")
         self._algo_name = algo_name
@@ -54,7 +55,17 @@ class CFRBase:
         """One engine per stack size.  Two-card games launched under torch.distributed (one process per GPU) shard their
         boards over the ranks (pokerrl_b200.distributed); everything else runs on this process's GPU."""
         import torch.distributed as dist
-        if env_cls.RULES.N_HOLE_CARDS == 2 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if device is None and multi:  # one process per GPU: this rank's device, not cuda:0
+            import os
+            device = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+        from pokerrl_b200 import board_engine
+        if board_engine.supports(env_cls, env_args, self._SOLVER_ALGO):
+            # one chance layer with the compiled post-deal shape (Flop5Holdem): board-resident fused sweeps
+            return board_engine.BoardCFRSolver(env_cls, env_args, board_spec, algo=self._SOLVER_ALGO, delay=delay,
+                                               device=device, rank=dist.get_rank() if multi else 0,
+                                               world=dist.get_world_size() if multi else 1)
+        if env_cls.RULES.N_HOLE_CARDS == 2 and multi:
             from pokerrl_b200.distributed import ShardedCFRSolver
             from pokerrl_b200.game.holdem_boards import BoardSpec
             spec = board_spec if board_spec is not None else BoardSpec.full_game(env_cls.RULES)

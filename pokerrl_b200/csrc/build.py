@@ -22,6 +22,7 @@ SOURCES = {
     "cfr_levels.cu": ["-fmad=false"],
     "hand_eval.cu": [],
     "cfr_twocard.cu": [],
+    "cfr_board.cu": ["--expt-relaxed-constexpr"],
     "env_kernels.cu": [],
 }
 

@@ -1,0 +1,714 @@
+// Board-resident CFR+ sweeps for two-hole-card games with ONE chance layer (Flop5Holdem, PokerRL/game/games.py:222-254) - sm_100a.
+//
+// The level-synchronous sweeps (cfr_twocard.cu) spill every node vector of every board subtree to HBM: 186 GB per
+// iteration against 40 GB of regret / average tables.  Here ONE persistent CTA walks whole (board, seat)
+// units: the 15-node post-deal subtree of a board lives in registers / shared memory, HBM sees only
+//     opponent regret rows (strategy by regret matching)  ->  reach of the opponent, top-down        (P1)
+//     9 terminal rows (5 showdown + 4 fold) evaluated together in shared memory                      (P2)
+//     own regret + average rows read, updated, written; the board's root value accumulated into the
+//     chance-node sum as 64-bit FIXED POINT (exactly associative: any grouping over CTAs / GPUs gives
+//     the same bits)                                                                                 (P3)
+// Rows of a board's table are stored in the board's STRENGTH ORDER and hold only the 1081 hands that do not collide
+// with the board (stride 1088 floats instead of 1326 natural-order entries): showdown prefix sums run over consecutive
+// addresses, blocked hands cost nothing, 18 % fewer bytes.  The per-board index tables (15 KB: packed per-hand record,
+// hand ids, card rows) are staged by cp.async.bulk (TMA 1-D bulk copies) completing on mbarriers, the next board's tables
+// in flight while the current board computes.
+//
+// Arithmetic follows the reference statements generalised to two-card hands (float64 restatement
+// in oracle/cfr2_oracle.c): reach StrategyFiller.py:118-146, 159-166; fold / showdown values ValueFiller.py:103-158;
+// value backup :64-93; regrets _CFRBase.py:146-185 + CFRPlus.py:37-41; regret matching CFRPlus.py:43-63; averaging
+// CFRPlus.py:65-87.  The strategy is never stored: it is a pure function of the regret rows (CFRPlus.py:49-58).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+#include "pokerrl_b200.h"
+#include "prl_common.cuh"
+
+namespace {
+
+// ---- geometry of a 52-card deck with a complete 5-card board
+constexpr int kDeck = 52;
+constexpr int kBoardCards = 5;
+constexpr int kLiveCards = kDeck - kBoardCards;            // 47
+constexpr int kLive = kLiveCards * (kLiveCards - 1) / 2;   // 1081 hands that hold no board card
+constexpr int kLdb = 1088;                                  // row stride (floats) of the strength-ordered tables
+constexpr int kRowLen = kLiveCards - 1;                     // 46 live hands hold a given live card
+constexpr int kRowPad = 48;                                 // card rows padded to 4 lanes x 12 entries
+constexpr int kRowSeg = 12;
+constexpr int kErStride = kLiveCards;                       // centred prefix array of a card row: entries 0..46
+constexpr int kZeroSlot = kLive + 1;                        // S[v][1082] is always 0 (target of the row padding)
+constexpr int kRange = 1326;
+
+// per-board table blob (bytes): packed records, hand ids, card rows
+constexpr int kRecBytes = kLdb * 8;                         // uint64 per strength position
+constexpr int kShBytes = kLdb * 2;                          // int16 hand id per strength position
+constexpr int kRowIdxBytes = kLiveCards * kRowPad * 2;      // int16 strength position per card-row entry
+constexpr int kBlobA = kRecBytes + kShBytes;                // 10 880 B, needed by P1 and P3
+constexpr int kBlobBytes = kBlobA + kRowIdxBytes;           // 15 392 B
+static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+constexpr int kThreads = 448;  // 14 warps; 3 strength positions per thread (2 * 448 + 185)
+constexpr int kPerThread = 3;
+constexpr int kWarps = kThreads / 32;
+
+// ---- compiled shape of the post-deal subtree (breadth-first; Flop5Holdem with pot-size raises, stacks that allow the
+//      full raise sequence).  The host checks the game's abstract tree against these arrays.
+struct ShapeFHP {
+    static constexpr int N = 15;
+    static constexpr int kind(int i) { constexpr int a[N] = {1, 0, 0, 4, 1, 3, 4, 1, 3, 4, 0, 3, 4, 3, 4}; return a[i]; }
+    static constexpr int parent(int i) { constexpr int a[N] = {-1, 0, 0, 1, 1, 2, 2, 2, 4, 4, 4, 7, 7, 10, 10}; return a[i]; }
+    static constexpr int first_child(int i) { constexpr int a[N] = {1, 3, 5, -1, 8, -1, -1, 11, -1, -1, 13, -1, -1, -1, -1}; return a[i]; }
+    static constexpr int n_children(int i) { constexpr int a[N] = {2, 2, 3, 0, 3, 0, 0, 2, 0, 0, 2, 0, 0, 0, 0}; return a[i]; }
+    // index of terminal i among the showdown / fold vectors
+    static constexpr int vec_index(int i) {
+        int n = 0;
+        for (int k = 0; k < i; ++k) n += (kind(k) == kind(i));
+        return n;
+    }
+    static constexpr int count(int k) {
+        int n = 0;
+        for (int i = 0; i < N; ++i) n += (kind(i) == k);
+        return n;
+    }
+    static constexpr int n_sd = 5, n_fold = 4;
+    // index of decision node i among the decision nodes (table row groups)
+    static constexpr int dec_index(int i) {
+        int n = 0;
+        for (int k = 0; k < i; ++k) n += (kind(k) <= 1);
+        return n;
+    }
+    static constexpr int n_dec = 6;
+};
+static_assert(ShapeFHP::count(4) == ShapeFHP::n_sd && ShapeFHP::count(3) == ShapeFHP::n_fold, "shape");
+static_assert(ShapeFHP::count(0) + ShapeFHP::count(1) == ShapeFHP::n_dec, "shape");
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for_down(F&& f) {  // N-1 .. I
+    if constexpr (I < N) {
+        f(std::integral_constant<int, N - 1>{});
+        static_for_down<I, N - 1>(f);
+    }
+}
+
+// ---- shared memory carve-up (bytes)
+constexpr int kNVec = ShapeFHP::n_sd + ShapeFHP::n_fold;                   // 9 terminal vectors
+constexpr int kSOff = 0;                                                    // float S[9][1088]
+constexpr int kErOff = kSOff + kNVec * kLdb * 4;                            // float Er[5][47*47]
+constexpr int kErVec = kLiveCards * kErStride;                              // 2209 floats per showdown vector
+constexpr int kErBytes = ((ShapeFHP::n_sd * kErVec * 4) + 15) & ~15;
+constexpr int kBlobOff = kErOff + kErBytes;                                 // 2 x (rec + hand ids)
+constexpr int kRowIdxOff = kBlobOff + 2 * kBlobA;                           // card rows (single buffer)
+constexpr int kCsOff = kRowIdxOff + kRowIdxBytes;                           // float cs[4][48] per-card sums of the fold vectors
+constexpr int kMiscOff = kCsOff + ShapeFHP::n_fold * kRowPad * 4;           // float wsum[5][16], wexc[5][16], tot[5], tf[4]
+constexpr int kMiscBytes = (5 * 16 + 5 * 16 + 8 + 8) * 4;
+constexpr int kBarOff = kMiscOff + kMiscBytes;                              // 3 mbarriers
+constexpr int kSmemBytes = kBarOff + 32;
+static_assert(kBlobOff % 16 == 0 && kRowIdxOff % 16 == 0 && kBarOff % 8 == 0, "alignment");
+static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
+
+struct SweepArgs {
+    prl_board_game_t g;
+    const float* trunk_reach_opp;  // natural order row of the opponent's reach at the chance node
+    int iter, delay;
+    float m_old, m_new;            // CFRPlus.py:68-73
+    int src_own, src_opp;          // evaluation: 0 = regret matching of `regret`, 1 = `avg` rows as they are
+    double fx_scale;               // 2^frac_bits
+};
+
+// ---- PTX helpers: mbarrier + 1-D bulk copy global -> shared (TMA), sm_90+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// strategy of one decision node from its table rows: regret matching (CFRPlus.py:43-63; the regrets of Vanilla / Linear
+// CFR are clipped first, LinearCFR.py:33-51) or the rows as they are (CFR+ average strategy)
+template <int A>
+__device__ __forceinline__ void node_strategy(const float (&g)[A], int src, float (&s)[A]) {
+    if (src == 1) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) s[a] = g[a];
+        return;
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        s[a] = fmaxf(g[a], 0.0f);
+        sum += s[a];
+    }
+    const float inv = (sum > 0.0f) ? 1.0f / sum : 0.0f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) s[a] = (sum > 0.0f) ? s[a] * inv : 1.0f / (float)A;
+}
+
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+// =====================================================================================================================
+// The sweep kernel.  P = seat whose values are computed; EVAL = false: CFR+ update of seat P (regrets, average);
+// EVAL = true: values and best-response values of seat P under the strategies selected by src_own / src_opp.
+// =====================================================================================================================
+template <class SH, int P, bool EVAL>
+__global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* S = reinterpret_cast<float*>(smem + kSOff);
+    float* Er = reinterpret_cast<float*>(smem + kErOff);
+    float* cs = reinterpret_cast<float*>(smem + kCsOff);
+    float* wsum = reinterpret_cast<float*>(smem + kMiscOff);  // [5][16] warp totals of the main scans
+    float* wexc = wsum + 5 * 16;                               // [5][16] exclusive prefix of the warp totals
+    float* tot = wexc + 5 * 16;                                // [8]     totals of the showdown vectors
+    float* tf = tot + 8;                                       // [8]     totals of the fold vectors
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);  // [0], [1]: blob A buffers; [2]: card rows
+    const int16_t* rowidx = reinterpret_cast<const int16_t*>(smem + kRowIdxOff);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const prl_board_game_t& G = a.g;
+    const int nb = G.n_boards;
+    constexpr int OPP = 1 - P;
+    constexpr int NSD = SH::n_sd, NF = SH::n_fold;
+    const unsigned char* blob_g = reinterpret_cast<const unsigned char*>(G.tables);
+
+    // private chance-sum accumulators of this CTA (global, L2-resident): [2][kRange] int64
+    long long* wp = reinterpret_cast<long long*>(G.w_private) + (size_t)blockIdx.x * 2 * kRange;
+    for (int h = tid; h < 2 * kRange; h += kThreads) wp[h] = 0;
+    for (int v = 0; v < kNVec; ++v)
+        for (int i = kLive + tid; i < kLdb; i += kThreads) S[v * kLdb + i] = 0.0f;  // incl. the always-zero slot
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        fence_async_shared();
+    }
+    __syncthreads();
+    int j = blockIdx.x;
+    if (tid == 0 && j < nb) {  // first board's tables
+        mbar_expect_tx(&bars[0], kBlobA);
+        bulk_g2s(smem + kBlobOff, blob_g + (size_t)j * kBlobBytes, kBlobA, &bars[0]);
+        mbar_expect_tx(&bars[2], kRowIdxBytes);
+        bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)j * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
+    }
+
+    for (int it = 0; j < nb; j += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const unsigned char* blob = smem + kBlobOff + buf * kBlobA;
+        const uint64_t* rec = reinterpret_cast<const uint64_t*>(blob);
+        const int16_t* sh = reinterpret_cast<const int16_t*>(blob + kRecBytes);
+        const int jn = j + gridDim.x;
+        if (tid == 0 && jn < nb) {  // next board's records + hand ids into the other buffer (free since the last barrier)
+            mbar_expect_tx(&bars[buf ^ 1], kBlobA);
+            bulk_g2s(smem + kBlobOff + (buf ^ 1) * kBlobA, blob_g + (size_t)jn * kBlobBytes, kBlobA, &bars[buf ^ 1]);
+        }
+        const float prob = __ldg(G.board_prob + j);
+        mbar_wait(&bars[buf], (it >> 1) & 1);
+
+        // ------------------------------------------------------------------------------------------ P1: reach, top-down
+        // x[i] = reach of the OPPONENT at local node i (StrategyFiller.py:118-146); terminal rows go to S in strength order
+#pragma unroll 1
+        for (int k = 0; k < kPerThread; ++k) {
+            const int i = tid + k * kThreads;
+            if (i >= kLive) break;
+            const int hand = sh[i];
+            float x[SH::N];
+            x[0] = __ldg(a.trunk_reach_opp + hand) * prob;  // the deal (StrategyFiller.py:137-140); blocked hands are not stored
+            static_for<0, SH::N>([&](auto I) {
+                constexpr int n = decltype(I)::value;
+                constexpr int A = SH::n_children(n);
+                if constexpr (SH::kind(n) <= 1) {
+                    constexpr int fc = SH::first_child(n);
+                    if constexpr (SH::kind(n) == OPP) {
+                        const float* tab = (EVAL && a.src_opp == 1) ? G.avg : G.regret;
+                        const float* row = tab + ((size_t)G.row0[fc] + (size_t)j * A) * kLdb + i;
+                        float g[A], s[A];
+#pragma unroll
+                        for (int c = 0; c < A; ++c) g[c] = ld_stream(row + (size_t)c * kLdb);
+                        node_strategy<A>(g, EVAL ? a.src_opp : 0, s);
+#pragma unroll
+                        for (int c = 0; c < A; ++c) x[fc + c] = x[n] * s[c];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < A; ++c) x[fc + c] = x[n];
+                    }
+                } else if constexpr (SH::kind(n) == 4) {
+                    S[SH::vec_index(n) * kLdb + i] = x[n];
+                } else {
+                    S[(NSD + SH::vec_index(n)) * kLdb + i] = x[n];
+                }
+            });
+        }
+        __syncthreads();  // B1: S complete
+
+        // ------------------------------------------------------------------------------------------ P2a: card rows
+        // quad (live card lc, lane q): entries [12 q, 12 q + 12) of the card's row in strength order.  Showdown vectors:
+        // centred exclusive prefix sums Er[v][lc][k] = (mass of the k weakest hands holding the card) - half the row's mass;
+        // fold vectors: the row's mass cs[f][lc].
+        mbar_wait(&bars[2], it & 1);
+        if (tid < kLiveCards * 4) {
+            const int lc = tid >> 2, q = tid & 3;
+            const uint2* rp = reinterpret_cast<const uint2*>(rowidx + lc * kRowPad + q * kRowSeg);
+            const uint2 w0 = rp[0], w1 = rp[1], w2 = rp[2];
+            const unsigned pk[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+            int idx[kRowSeg];
+#pragma unroll
+            for (int e = 0; e < kRowSeg; ++e) idx[e] = (pk[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+#pragma unroll 1
+            for (int v = 0; v < NSD; ++v) {
+                const float* Sv = S + v * kLdb;
+                float inc[kRowSeg];
+                float run = 0.0f;
+#pragma unroll
+                for (int e = 0; e < kRowSeg; ++e) {
+                    inc[e] = run;
+                    run += Sv[idx[e]];
+                }
+                float sc = run;  // inclusive scan over the quad
+                float t = __shfl_up_sync(0xffffffffu, sc, 1, 4);
+                if (q >= 1) sc += t;
+                t = __shfl_up_sync(0xffffffffu, sc, 2, 4);
+                if (q >= 2) sc += t;
+                const float half = 0.5f * __shfl_sync(0xffffffffu, sc, 3, 4);
+                const float off = (sc - run) - half;
+                float* row = Er + v * kErVec + lc * kErStride + q * kRowSeg;
+#pragma unroll
+                for (int e = 0; e < kRowSeg; ++e)
+                    if (q * kRowSeg + e < kErStride) row[e] = off + inc[e];
+            }
+#pragma unroll 1
+            for (int f = 0; f < NF; ++f) {
+                const float* Sv = S + (NSD + f) * kLdb;
+                float run = 0.0f;
+#pragma unroll
+                for (int e = 0; e < kRowSeg; ++e) run += Sv[idx[e]];
+                run += __shfl_xor_sync(0xffffffffu, run, 1, 4);
+                run += __shfl_xor_sync(0xffffffffu, run, 2, 4);
+                if (q == 0) cs[f * kRowPad + lc] = run;
+            }
+        }
+        __syncthreads();  // B2: card rows done, S may be overwritten, the row table may be replaced
+        if (tid == 0 && jn < nb) {
+            mbar_expect_tx(&bars[2], kRowIdxBytes);
+            bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)jn * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
+        }
+
+        // ------------------------------------------------------------------------------------------ P2b: main scans
+        // centred exclusive prefix sums over the strength order, in place: E[k] = (mass of the k weakest hands) - total / 2,
+        // k = 0 .. 1081.  Thread t owns positions 3t .. 3t+2; double accumulation inside a thread and across warps.
+        float a0[NSD], a1[NSD], a2[NSD], pre[NSD];
+        {
+            const int b0 = 3 * tid;
+#pragma unroll
+            for (int v = 0; v < NSD; ++v) {
+                const float* Sv = S + v * kLdb;
+                a0[v] = (b0 < kLive) ? Sv[b0] : 0.0f;
+                a1[v] = (b0 + 1 < kLive) ? Sv[b0 + 1] : 0.0f;
+                a2[v] = (b0 + 2 < kLive) ? Sv[b0 + 2] : 0.0f;
+                const float loc = (a0[v] + a1[v]) + a2[v];
+                float incw = loc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float t = __shfl_up_sync(0xffffffffu, incw, o);
+                    if (lane >= o) incw += t;
+                }
+                pre[v] = incw - loc;  // exclusive within the warp
+                if (lane == 31) wsum[v * 16 + warp] = incw;
+            }
+        }
+        __syncthreads();  // B3
+        if (warp == 0) {
+#pragma unroll
+            for (int v = 0; v < NSD; ++v) {  // exclusive scan of the 14 warp totals (double: 14 terms of a large sum)
+                const double w = (lane < kWarps) ? (double)wsum[v * 16 + lane] : 0.0;
+                double sc = w;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, sc, o);
+                    if (lane >= o) sc += t;
+                }
+                const double total = __shfl_sync(0xffffffffu, sc, kWarps - 1);
+                if (lane < kWarps) wexc[v * 16 + lane] = (float)((sc - w) - 0.5 * total);
+                if (lane == 0) tot[v] = (float)total;
+            }
+        } else if (warp == 1) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {  // total of a fold vector = half the sum of its card rows
+                float s2 = ((lane < kLiveCards) ? cs[f * kRowPad + lane] : 0.0f) +
+                           ((lane + 32 < kLiveCards) ? cs[f * kRowPad + lane + 32] : 0.0f);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                if (lane == 0) tf[f] = 0.5f * s2;
+            }
+        }
+        __syncthreads();  // B3b
+        {
+            const int b0 = 3 * tid;
+#pragma unroll
+            for (int v = 0; v < NSD; ++v) {
+                float* Sv = S + v * kLdb;
+                float run = pre[v] + wexc[v * 16 + warp];
+                if (b0 <= kLive) Sv[b0] = run;
+                run += a0[v];
+                if (b0 + 1 <= kLive) Sv[b0 + 1] = run;
+                run += a1[v];
+                if (b0 + 2 <= kLive) Sv[b0 + 2] = run;
+            }
+        }
+        __syncthreads();  // B4: prefix arrays complete
+
+        // ------------------------------------------------------------------------------------------ P3: values, bottom-up
+        const float mult = __ldg(G.board_mult + j);
+        const double fx = (double)mult * a.fx_scale;
+#pragma unroll 1
+        for (int k = 0; k < kPerThread; ++k) {
+            const int i = tid + k * kThreads;
+            if (i >= kLive) break;
+            const uint64_t w = rec[i];
+            const int gs = (int)(w & 0x7ffu), ge = (int)((w >> 11) & 0x7ffu);
+            const int lc1 = (int)((w >> 22) & 0x3fu), lc2 = (int)((w >> 28) & 0x3fu);
+            const int o1 = lc1 * kErStride + (int)((w >> 34) & 0x3fu), o1e = o1 + (int)((w >> 40) & 0x3fu);
+            const int o2 = lc2 * kErStride + (int)((w >> 46) & 0x3fu), o2e = o2 + (int)((w >> 52) & 0x3fu);
+            const int hand = sh[i];
+            long long* wacc = wp + hand;
+            const long long w_ev = *wacc;  // requested early, consumed at the end
+            long long w_br = 0;
+            if constexpr (EVAL) w_br = wacc[kRange];
+            float e[SH::N], br[EVAL ? SH::N : 1];
+            // terminal rows (ValueFiller.py:103-158): ev = equity * K * pot / 2, the folder loses
+            static_for<0, SH::N>([&](auto I) {
+                constexpr int n = decltype(I)::value;
+                if constexpr (SH::kind(n) == 4) {
+                    constexpr int v = SH::vec_index(n);
+                    const float* Ev = S + v * kLdb;
+                    const float* Rv = Er + v * kErVec;
+                    const float all = Ev[gs] + Ev[ge];
+                    const float rows = (Rv[o1] + Rv[o1e]) + (Rv[o2] + Rv[o2e]);
+                    e[n] = (all - rows) * (G.eq_const * G.pot[n] * 0.5f);
+                    if constexpr (EVAL) br[n] = e[n];
+                } else if constexpr (SH::kind(n) == 3) {
+                    constexpr int f = SH::vec_index(n);
+                    const float mass = ((tf[f] - cs[f * kRowPad + lc1]) - cs[f * kRowPad + lc2]) + S[(NSD + f) * kLdb + i];
+                    const float sc = G.eq_const * G.pot[n] * 0.5f;
+                    e[n] = mass * ((G.acted_last[n] == P) ? -sc : sc);
+                    if constexpr (EVAL) br[n] = e[n];
+                }
+            });
+            // decision nodes, deepest first (ValueFiller.py:64-93); regrets / matching / average at P's nodes
+            static_for_down<0, SH::N>([&](auto I) {
+                constexpr int n = decltype(I)::value;
+                constexpr int A = SH::n_children(n);
+                if constexpr (SH::kind(n) <= 1) {
+                    constexpr int fc = SH::first_child(n);
+                    if constexpr (SH::kind(n) == OPP) {
+                        float v = e[fc];
+#pragma unroll
+                        for (int c = 1; c < A; ++c) v += e[fc + c];
+                        e[n] = v;
+                        if constexpr (EVAL) {
+                            float b = br[fc];
+#pragma unroll
+                            for (int c = 1; c < A; ++c) b += br[fc + c];
+                            br[n] = b;
+                        }
+                    } else {
+                        const size_t r0 = ((size_t)G.row0[fc] + (size_t)j * A) * kLdb + i;
+                        float g[A], s[A];
+                        if constexpr (EVAL) {
+                            const float* tab = (a.src_own == 1) ? G.avg : G.regret;
+#pragma unroll
+                            for (int c = 0; c < A; ++c) g[c] = ld_stream(tab + r0 + (size_t)c * kLdb);
+                            node_strategy<A>(g, a.src_own, s);
+                            float v = s[0] * e[fc], b = br[fc];
+#pragma unroll
+                            for (int c = 1; c < A; ++c) {
+                                v += s[c] * e[fc + c];
+                                b = fmaxf(b, br[fc + c]);
+                            }
+                            e[n] = v;
+                            br[n] = b;
+                        } else {
+                            float av[A];
+#pragma unroll
+                            for (int c = 0; c < A; ++c) g[c] = ld_stream(G.regret + r0 + (size_t)c * kLdb);
+                            const bool do_avg = a.iter >= a.delay;
+                            if (do_avg && a.m_old != 0.0f) {
+#pragma unroll
+                                for (int c = 0; c < A; ++c) av[c] = ld_stream(G.avg + r0 + (size_t)c * kLdb);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < A; ++c) av[c] = 0.0f;
+                            }
+                            node_strategy<A>(g, 0, s);
+                            float v = s[0] * e[fc];
+#pragma unroll
+                            for (int c = 1; c < A; ++c) v += s[c] * e[fc + c];
+                            e[n] = v;
+#pragma unroll
+                            for (int c = 0; c < A; ++c) g[c] = fmaxf((e[fc + c] - v) + g[c], 0.0f);  // CFRPlus.py:37-41
+                            node_strategy<A>(g, 0, s);
+#pragma unroll
+                            for (int c = 0; c < A; ++c) st_stream(G.regret + r0 + (size_t)c * kLdb, g[c]);
+                            if (do_avg) {  // CFRPlus.py:65-87 (not reach-weighted)
+#pragma unroll
+                                for (int c = 0; c < A; ++c)
+                                    st_stream(G.avg + r0 + (size_t)c * kLdb, a.m_old * av[c] + a.m_new * s[c]);
+                            }
+                        }
+                    }
+                }
+            });
+            // the board's contribution to its parent's sum (ValueFiller.py:76-78), 64-bit fixed point
+            *wacc = w_ev + __double2ll_rn((double)e[0] * fx);
+            if constexpr (EVAL) wacc[kRange] = w_br + __double2ll_rn((double)br[0] * fx);
+        }
+        __syncthreads();  // B5: S / Er / tables of this board are free
+    }
+    // merge into the device-wide sums (integer adds: exact in any order)
+    __syncthreads();
+    unsigned long long* wt = reinterpret_cast<unsigned long long*>(G.w_total);
+    for (int h = tid; h < (EVAL ? 2 : 1) * kRange; h += kThreads) {
+        const long long v = wp[h];
+        if (v != 0) atomicAdd(wt + h, (unsigned long long)v);
+    }
+}
+
+// =====================================================================================================================
+// Per-board tables from the hand strengths (prl_hand_rank_boards): strength order, packed records, card rows.
+// One CTA per board.  blob layout: uint64 rec[1088] | int16 hand[1088] | int16 rowidx[47][48]
+//   rec[s] (s = strength position, ties ordered by hand id): bits 0-10 gs (# strictly weaker), 11-21 ge (# weaker or equal),
+//          22-27 / 28-33 compact index of the hand's first / second card among the 47 live cards, 34-39 # hands of the first
+//          card's row strictly weaker, 40-45 # tied in that row (incl. the hand itself), 46-51 / 52-57 same for the second card
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) board_tables_kernel(const int32_t* __restrict__ ranks, const uint64_t* __restrict__ board_mask,
+                                                           const int8_t* __restrict__ hand_cards, int n_boards,
+                                                           unsigned char* __restrict__ out) {
+    __shared__ int srk[kRange];
+    __shared__ short spos[kRange], sgs[kRange], sge[kRange];
+    const int b = blockIdx.x;
+    const uint64_t bm = board_mask[b];
+    unsigned char* blob = out + (size_t)b * kBlobBytes;
+    uint64_t* rec = reinterpret_cast<uint64_t*>(blob);
+    int16_t* sh = reinterpret_cast<int16_t*>(blob + kRecBytes);
+    int16_t* rowidx = reinterpret_cast<int16_t*>(blob + kBlobA);
+    for (int h = threadIdx.x; h < kRange; h += blockDim.x) srk[h] = ranks[(size_t)b * kRange + h];
+    for (int i = threadIdx.x; i < kLdb; i += blockDim.x) {
+        rec[i] = 0;
+        sh[i] = 0;
+    }
+    for (int i = threadIdx.x; i < kLiveCards * kRowPad; i += blockDim.x) rowidx[i] = (int16_t)kZeroSlot;
+    __syncthreads();
+    for (int h = threadIdx.x; h < kRange; h += blockDim.x) {
+        const int r = srk[h];
+        int lt = 0, le = 0, tb = 0;
+        if (r >= 0) {
+            for (int q = 0; q < kRange; ++q) {
+                const int x = srk[q];
+                if (x < 0) continue;
+                lt += x < r;
+                le += x <= r;
+                tb += (x == r) && (q < h);
+            }
+        }
+        sgs[h] = (short)(r >= 0 ? lt : -1);
+        sge[h] = (short)(r >= 0 ? le : -1);
+        spos[h] = (short)(r >= 0 ? lt + tb : -1);
+    }
+    __syncthreads();
+    // card rows: item (card c, other card x)
+    for (int it = threadIdx.x; it < kDeck * (kDeck - 1); it += blockDim.x) {
+        const int c = it / (kDeck - 1), xr = it % (kDeck - 1);
+        const int x = xr + (xr >= c);
+        if (((bm >> c) | (bm >> x)) & 1ull) continue;
+        const int c1 = min(c, x), c2 = max(c, x);
+        const int h = c1 * (2 * kDeck - 1 - c1) / 2 + (c2 - c1 - 1);
+        const int g = sgs[h], ps = spos[h];
+        int lt = 0, le = 0, kpos = 0;
+        for (int y = 0; y < kDeck; ++y) {
+            if (y == c || ((bm >> y) & 1ull)) continue;
+            const int d1 = min(c, y), d2 = max(c, y);
+            const int h2 = d1 * (2 * kDeck - 1 - d1) / 2 + (d2 - d1 - 1);
+            const int g2 = sgs[h2];
+            lt += g2 < g;
+            le += g2 <= g;
+            kpos += spos[h2] < ps;
+        }
+        const int lc = c - __popcll(bm & ((1ull << c) - 1ull));
+        rowidx[lc * kRowPad + kpos] = (int16_t)ps;
+        // this card's fields of the hand's record (first card = the smaller id)
+        const uint64_t fld = ((uint64_t)lc) << (c == c1 ? 22 : 28) | ((uint64_t)lt) << (c == c1 ? 34 : 46) |
+                             ((uint64_t)(le - lt)) << (c == c1 ? 40 : 52);
+        atomicOr(reinterpret_cast<unsigned long long*>(rec + ps), (unsigned long long)fld);
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < kRange; h += blockDim.x) {
+        const int ps = spos[h];
+        if (ps < 0) continue;
+        sh[ps] = (int16_t)h;
+        atomicOr(reinterpret_cast<unsigned long long*>(rec + ps),
+                 (unsigned long long)((uint64_t)sgs[h] | ((uint64_t)sge[h] << 11)));
+    }
+}
+
+// chance-node rows from the fixed-point sums: out[a][h] = 2^-frac * sum over the suit permutations s of W[a][s(h)]
+// (integer sum: exact), or W[a][h] itself without isomorphism (suit symmetrisation)
+__global__ void board_collect_kernel(const long long* __restrict__ w_total, int n_arr, const int16_t* __restrict__ sym_perm,
+                                     int n_sym, double inv_scale, float* __restrict__ out, int ld) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= kRange) return;
+    for (int a = 0; a < n_arr; ++a) {
+        long long s = 0;
+        if (n_sym > 1) {
+            for (int q = 0; q < n_sym; ++q) s += w_total[(size_t)a * kRange + sym_perm[(size_t)q * kRange + h]];
+        } else {
+            s = w_total[(size_t)a * kRange + h];
+        }
+        out[(size_t)a * ld + h] = (float)((double)s * inv_scale);
+    }
+}
+
+// strength-ordered rows <-> natural-order rows of ONE table (interfaces to the level engine, checkpoints, agents)
+__global__ void board_permute_kernel(const unsigned char* __restrict__ tables, int n_boards, int rows_per_board,
+                                     const int64_t* __restrict__ row_src, const int64_t* __restrict__ row_dst, float* sorted_tab,
+                                     float* natural_tab, int ld, int to_natural) {
+    // block = (board j, row r of the board); row_src[r] / row_dst[r]: row index on board 0 and stride per board packed
+    const int j = blockIdx.x / rows_per_board, r = blockIdx.x % rows_per_board;
+    const int16_t* sh = reinterpret_cast<const int16_t*>(tables + (size_t)j * kBlobBytes + kRecBytes);
+    float* srow = sorted_tab + ((size_t)row_src[2 * r] + (size_t)j * row_src[2 * r + 1]) * kLdb;
+    float* nrow = natural_tab + ((size_t)row_dst[2 * r] + (size_t)j * row_dst[2 * r + 1]) * ld;
+    if (to_natural) {
+        for (int h = threadIdx.x; h < ld; h += blockDim.x) nrow[h] = 0.0f;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kLive; i += blockDim.x) nrow[sh[i]] = srow[i];
+    } else {
+        for (int i = threadIdx.x; i < kLive; i += blockDim.x) srow[i] = nrow[sh[i]];
+    }
+}
+
+bool shape_matches(const prl_board_game_t* g) {
+    if (g->n_local != ShapeFHP::N) return false;
+    for (int i = 0; i < ShapeFHP::N; ++i)
+        if (g->kind[i] != ShapeFHP::kind(i) || g->parent[i] != ShapeFHP::parent(i) || g->first_child[i] != ShapeFHP::first_child(i) ||
+            g->n_children[i] != ShapeFHP::n_children(i))
+            return false;
+    return true;
+}
+
+int default_grid() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = 2 * sms;
+    }
+    return cached[dev];
+}
+
+template <int P, bool EVAL>
+int launch_sweep(const SweepArgs& a, int grid, cudaStream_t s) {
+    auto kern = board_sweep_kernel<ShapeFHP, P, EVAL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);  // per device: set every time
+    if (e != cudaSuccess) return prl::check(e, "prl_board_sweep: shared memory opt-in");
+    kern<<<grid, kThreads, kSmemBytes, s>>>(a);
+    prl::count_launch();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int prl_board_layout(int32_t* out) {
+    out[0] = kLive;
+    out[1] = kLdb;
+    out[2] = kBlobBytes;
+    out[3] = kRecBytes;            // offset of the hand ids inside a board's blob
+    out[4] = kBlobA;               // offset of the card rows
+    out[5] = kLiveCards;
+    out[6] = kRowPad;
+    out[7] = ShapeFHP::N;
+    return 0;
+}
+
+extern "C" int prl_board_grid(void) { return default_grid(); }
+
+extern "C" int prl_board_shape_ok(const prl_board_game_t* g) { return (g && shape_matches(g)) ? 1 : 0; }
+
+extern "C" int prl_board_build_tables(const int32_t* ranks, const uint64_t* board_mask, const int8_t* hand_cards, int n_boards,
+                                      void* blob, prl_stream_t stream) {
+    if (n_boards <= 0) return 0;
+    board_tables_kernel<<<n_boards, 256, 0, (cudaStream_t)stream>>>(ranks, board_mask, hand_cards, n_boards, (unsigned char*)blob);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_board_build_tables");
+}
+
+extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int src_own, int src_opp, const float* trunk_reach_opp,
+                               int iter, int delay, prl_stream_t stream) {
+    if (!g || !shape_matches(g)) return prl::fail("prl_board_sweep: the post-deal subtree does not have the compiled shape");
+    if (g->n_range != kRange || g->n_deck != kDeck) return prl::fail("prl_board_sweep: 52-card deck / 1326 hands only");
+    if (p < 0 || p > 1) return prl::fail("prl_board_sweep: bad seat");
+    if (!g->tables || !g->regret || !g->avg || !g->w_private || !g->w_total || !trunk_reach_opp)
+        return prl::fail("prl_board_sweep: missing buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = g->grid > 0 ? g->grid : default_grid();
+    SweepArgs a;
+    a.g = *g;
+    a.trunk_reach_opp = trunk_reach_opp;
+    a.iter = iter;
+    a.delay = delay;
+    const double cw = 0.5 * ((double)iter * (iter + 1) - (double)delay * (delay + 1));  // CFRPlus.py:68-73
+    const double nw = (double)iter - delay + 1;
+    a.m_old = (iter > delay) ? (float)(cw / (cw + nw)) : 0.0f;
+    a.m_new = (iter > delay) ? (float)(nw / (cw + nw)) : 1.0f;
+    a.src_own = src_own;
+    a.src_opp = src_opp;
+    a.fx_scale = (double)(1ull << g->frac_bits);
+    if (int e = prl::check(cudaMemsetAsync(g->w_total, 0, sizeof(long long) * 2 * kRange, s), "prl_board_sweep: memset")) return e;
+    int rc;
+    if (eval) rc = (p == 0) ? launch_sweep<0, true>(a, grid, s) : launch_sweep<1, true>(a, grid, s);
+    else rc = (p == 0) ? launch_sweep<0, false>(a, grid, s) : launch_sweep<1, false>(a, grid, s);
+    if (rc) return rc;
+    return prl::check(cudaGetLastError(), "prl_board_sweep");
+}
+
+extern "C" int prl_board_collect(const prl_board_game_t* g, int n_arr, const int16_t* sym_perm, int n_sym, float* out, int ld,
+                                 prl_stream_t stream) {
+    if (!g || n_arr < 1 || n_arr > 2) return prl::fail("prl_board_collect: bad arguments");
+    board_collect_kernel<<<(kRange + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long*>(g->w_total), n_arr, sym_perm, n_sym, 1.0 / (double)(1ull << g->frac_bits), out, ld);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_board_collect");
+}
+
+extern "C" int prl_board_permute(const prl_board_game_t* g, int rows_per_board, const int64_t* row_src, const int64_t* row_dst,
+                                 float* sorted_tab, float* natural_tab, int ld, int to_natural, prl_stream_t stream) {
+    if (!g || g->n_boards <= 0 || rows_per_board <= 0) return 0;
+    board_permute_kernel<<<g->n_boards * rows_per_board, 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned char*)g->tables, g->n_boards, rows_per_board, row_src, row_dst, sorted_tab, natural_tab, ld, to_natural);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_board_permute");
+}

@@ -1,0 +1,234 @@
+"""GPU parity of the board-resident CFR+ engine (csrc/cfr_board.cu, pokerrl_b200/board_engine.py), through the C ABI.
+
+Oracles: tests/golden/twocard_rows.npz (brute-force float64 terminal rows on hand strengths from the REFERENCE's
+lib_hand_eval.so) and oracle/cfr2_oracle.c (float64; pinned on those rows and on the numpy oracle).
+Tolerance (BASELINE.json north_star): 1e-6 relative on counterfactual values and exploitability for every single step from
+identical inputs (values under a given profile, one iteration from given tables); free-running trajectories are compared
+at the level the reference's own float32/float64 runs agree (SURVEY.md headline 5) and the achieved error is printed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cfr2_c
+from gen_golden_twocard_common import make_reach
+from pokerrl_b200.game.holdem_boards import BoardSpec
+from twocard_common import fhp_tree, oracle_ranks, random_board_spec
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "twocard_rows.npz"))
+TOL = 1e-6
+
+
+def _engine(spec, **kw):
+    from pokerrl_b200.board_engine import BoardCFRSolver
+    from pokerrl_b200.game import games
+    g = games.Flop5Holdem
+    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=[1.0])
+    return BoardCFRSolver(g, args, spec, **kw)
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_board_tables_decode_to_the_strength_order():
+    """packed records / hand ids / card rows of prl_board_build_tables against a host computation from the ranks"""
+    from pokerrl_b200.board_engine import board_layout
+    boards = GOLD["boards"][[0, 5, 121, 150, 199]]
+    s = _engine(BoardSpec(boards, np.ones(len(boards)), np.ones(len(boards)), None, "tables"))
+    L = board_layout()
+    blob = s.t_blob.cpu().numpy()
+    ranks = oracle_ranks(boards)
+    hc = np.asarray(s.game_cls.RULES.get_lut_holder().LUT_IDX_2_HOLE_CARDS).astype(np.int64)
+    for b in range(len(boards)):
+        rec = blob[b, :L["sh_off"]].view(np.uint64)
+        sh = blob[b, L["sh_off"]:L["rows_off"]].view(np.int16)
+        rows = blob[b, L["rows_off"]:].view(np.int16).reshape(L["live_cards"], L["row_pad"])
+        rk = ranks[b]
+        live = np.nonzero(rk >= 0)[0]
+        order = live[np.lexsort((live, rk[live]))]
+        assert np.array_equal(sh[:L["n_live"]], order)
+        srk = rk[order]
+        gs = np.searchsorted(srk, srk, side="left")
+        ge = np.searchsorted(srk, srk, side="right")
+        assert np.array_equal(rec[:L["n_live"]] & 0x7ff, gs) and np.array_equal((rec[:L["n_live"]] >> 11) & 0x7ff, ge)
+        live_cards = [c for c in range(52) if c not in boards[b]]
+        lc_of = {c: i for i, c in enumerate(live_cards)}
+        pos_of = {int(h): i for i, h in enumerate(order)}
+        for c in live_cards:
+            in_row = sorted(pos_of[int(h)] for h in order if c in hc[h])
+            assert list(rows[lc_of[c], :46]) == in_row and list(rows[lc_of[c], 46:]) == [L["n_live"] + 1] * 2
+        for i in (0, 17, 500, 1080):
+            h = order[i]
+            for k, (sl, st, sd) in enumerate(((22, 34, 40), (28, 46, 52))):
+                c = int(hc[h, k])
+                assert int((rec[i] >> np.uint64(sl)) & np.uint64(0x3f)) == lc_of[c]
+                row_ranks = np.array([rk[x] for x in live if c in hc[x]])
+                lt, le = int((row_ranks < rk[h]).sum()), int((row_ranks <= rk[h]).sum())
+                assert int((rec[i] >> np.uint64(st)) & np.uint64(0x3f)) == lt
+                assert int((rec[i] >> np.uint64(sd)) & np.uint64(0x3f)) == le - lt
+
+
+def test_root_rows_against_reference_anchored_golden_rows():
+    """One evaluation sweep per board with the golden opponent reach row as the trunk's reach and all regrets zero (uniform
+    strategies): the board's root value row is a fixed linear combination of the golden showdown and fold rows."""
+    import torch
+    from pokerrl_b200 import _native as nat
+    boards, K = GOLD["boards"], float(GOLD["eq_const"])
+    n = len(boards)
+    s = _engine(BoardSpec(boards, np.ones(n), np.ones(n), None, "golden rows"))
+    hc = np.asarray(s.game_cls.RULES.get_lut_holder().LUT_IDX_2_HOLE_CARDS).astype(np.int64)
+    reach = make_reach(int(GOLD["seed"]), boards, hc)
+    st = s.st
+    worst = {0: 0.0, 1: 0.0}
+    row = torch.zeros(s.ld, dtype=torch.float32, device=s.device)
+    for p in (0, 1):
+        # coefficients: every action has probability 1/A under zero regrets; own probabilities weight the value, opponent
+        # probabilities weight the reach (ValueFiller.py:64-93, StrategyFiller.py:118-146)
+        coef_sd, coef_fold = 0.0, 0.0
+        for t in range(st["n_local"]):
+            if st["kind"][t] < 3:
+                continue
+            w, i = 1.0, t
+            while st["parent"][i] >= 0:
+                w /= st["n_children"][st["parent"][i]]
+                i = st["parent"][i]
+            w *= st["pot"][t] / 2
+            if st["kind"][t] == 4:
+                coef_sd += w
+            else:
+                coef_fold += -w if st["acted_last"][t] == p else w
+        for b in range(n):
+            row[:1326] = torch.from_numpy(reach[b]).to(s.device)
+            s.t_mult.zero_()
+            s.t_mult[b] = 1.0
+            nat.call("prl_board_sweep", C.byref(s.g), p, 1, 0, 0, C.c_void_p(row.data_ptr()), 0, 0,
+                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            got = s.w_total[0].cpu().numpy().astype(np.float64) / 2.0 ** s.g.frac_bits
+            ref = coef_sd * GOLD["showdown"][b] + coef_fold * GOLD["fold"][b]
+            err = _rel(got, ref)
+            worst[p] = max(worst[p], err)
+            assert err <= TOL, (p, b, err)
+    print("board sweep root rows vs brute-force golden rows: worst relative error seat0 %.2e seat1 %.2e" % (worst[0], worst[1]))
+
+
+def _oracle(ft, **kw):
+    from twocard_common import oracle_tree
+    return cfr2_c.Oracle2CSolver(ft, oracle_tree(ft).board_ranks, "CFRPlus", n_threads=8, **kw)
+
+
+def _natural(s, ft):
+    reg, avg = s.natural_tables(ft)
+    return reg.cpu().numpy()[:, :ft.R].astype(np.float64), avg.cpu().numpy()[:, :ft.R].astype(np.float64)
+
+
+@pytest.mark.parametrize("iso", [False, True])
+def test_teacher_forced_steps_match_float64_oracle(iso):
+    """values / exploitability under given tables and ONE iteration from given tables, at 1e-6, along an oracle run"""
+    if iso:
+        from pokerrl_b200.game.games import FlopHoldemRules
+        spec = BoardSpec.full_game(FlopHoldemRules, isomorphic=True, deck_subset=[0, 1, 2, 3, 4, 5, 6, 7, 48, 49, 50, 51])
+    else:
+        spec = random_board_spec(48, 21)
+    ft = fhp_tree(spec)
+    orc = _oracle(ft, lean=True)
+    s = _engine(spec)
+    errs = []
+    for t in range(5):
+        # the engine starts every step from the oracle's tables (float32 copies)
+        s.load_natural_tables(ft, orc.regret, orc.avg)
+        s.set_trunk_strategy_from_regrets()
+        s.iter_counter = orc.iter_counter
+        a, b = s.exploitability_current(), orc.exploitability_current()
+        e1 = abs(a - b) / abs(b)
+        e2 = 0.0
+        if t > 0:
+            a, b = s.exploitability_average(), orc.exploitability_average()
+            e2 = abs(a - b) / abs(b)
+        s.iteration(1)
+        orc.iteration(1)
+        reg, avg = _natural(s, ft)
+        e3, e4 = _rel(reg, orc.regret), _rel(avg, orc.avg)
+        errs.append((e1, e2, e3, e4))
+        assert max(e1, e2, e3, e4) <= TOL, (t, e1, e2, e3, e4)
+    print("teacher-forced relative errors (expl current, expl average, regrets, average) per step:",
+          ["%.1e %.1e %.1e %.1e" % e for e in errs])
+
+
+def test_free_running_trajectory_and_level_engine():
+    """6 free-running iterations: board engine vs the float64 oracle vs the level engine (same game, three codes)"""
+    from pokerrl_b200.solver import CFRSolver
+    spec = random_board_spec(40, 5)
+    ft = fhp_tree(spec)
+    orc = _oracle(ft, lean=True)
+    s = _engine(spec)
+    lv = CFRSolver(ft, "CFRPlus")
+    a0, b0 = s.exploitability_current(), orc.exploitability_current()
+    assert abs(a0 - b0) <= TOL * abs(b0), (a0, b0)
+    out = []
+    for t in range(6):
+        s.iteration(1)
+        orc.iteration(1)
+        lv.iteration(1)
+        reg, _ = _natural(s, ft)
+        er = _rel(reg, orc.regret)
+        el = _rel(reg, lv.bufs.regret.cpu().numpy()[:, :ft.R].astype(np.float64))
+        a, b, c = s.exploitability_current(), orc.exploitability_current(), lv.exploitability_current()
+        x, y, z = s.exploitability_average(), orc.exploitability_average(), lv.exploitability_average()
+        out.append((er, el, abs(a - b) / abs(b), abs(x - y) / abs(y), abs(c - b) / abs(b)))
+        # regret matching amplifies round-off at near-zero regrets (SURVEY.md headline 5): trajectories are held to 1e-4
+        assert er <= 1e-4 and abs(a - b) <= 1e-4 * abs(b) and abs(x - y) <= 1e-4 * abs(y), (t, out[-1])
+        assert abs(z - y) <= 1e-4 * abs(y)
+    print("free-running (regret vs oracle, regret vs level engine, expl cur, expl avg, level-engine expl) per iteration:",
+          ["%.1e %.1e %.1e %.1e %.1e" % e for e in out])
+
+
+def test_fixed_point_sums_do_not_depend_on_the_grid():
+    """the chance-node sums are integers: any number of CTAs (and, by the same argument, of GPUs) gives the same bits"""
+    spec = random_board_spec(64, 33)
+    runs = []
+    for grid in (0, 7, 64):
+        s = _engine(spec, grid=grid)
+        s.iteration(3)
+        runs.append((s.regret.clone(), s.bufs.regret.clone(), s.exploitability_current(), s.exploitability_average()))
+    import torch
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1]) and r[2:] == runs[0][2:]
+
+
+def test_shards_reproduce_the_single_device_run_bit_for_bit():
+    """two 'ranks' on one device (boards round-robin), driven in lockstep with their integer sums added by hand in place of
+    the all-reduce, against one rank holding every board: identical tables, identical exploitability"""
+    import torch
+    spec = random_board_spec(30, 8)
+    one = _engine(spec)
+    parts = [_engine(spec, rank=r, world=2, reduce_fn=lambda t: None) for r in range(2)]
+    for it in range(3):
+        one.iteration(1)
+        for p in (0, 1):
+            for e in parts:
+                e._update_begin(p)
+            tot = parts[0].w_total + parts[1].w_total
+            for e in parts:
+                e.w_total.copy_(tot)
+                e._update_end(p)
+        for e in parts:
+            e.iter_counter += 1
+    ldb = one.regret.shape[1]
+    st = one.st
+    # row groups per decision node: [n_boards][A][ldb]
+    off1, offp = 0, [0, 0]
+    for d in [i for i in range(st["n_local"]) if st["kind"][i] <= 1]:
+        A = st["n_children"][d]
+        full = one.regret[off1:off1 + one.n_boards * A].view(one.n_boards, A, ldb)
+        full_avg = one.avg[off1:off1 + one.n_boards * A].view(one.n_boards, A, ldb)
+        off1 += one.n_boards * A
+        for r, e in enumerate(parts):
+            blk = e.regret[offp[r]:offp[r] + e.n_boards * A].view(e.n_boards, A, ldb)
+            blk_avg = e.avg[offp[r]:offp[r] + e.n_boards * A].view(e.n_boards, A, ldb)
+            offp[r] += e.n_boards * A
+            assert torch.equal(blk, full[r::2]) and torch.equal(blk_avg, full_avg[r::2]), (d, r)
+    for e in parts:
+        assert torch.equal(e.bufs.regret, one.bufs.regret) and torch.equal(e.bufs.avg, one.bufs.avg)
