@@ -129,17 +129,21 @@ class Oracle2CSolver:
         self.L.orc2_exploitability(C.byref(self.t), out.ctypes.data)
         return out
 
-    def iteration(self, n=1):
+    def half_iteration(self, p):
+        """seat p's part of an iteration (_CFRBase.py:123-128); the caller advances iter_counter after seat 1"""
         t = C.byref(self.t)
+        if self.lean:
+            self.L.orc2_values(t, self.strat.ctypes.data, 1 << p, 0)
+        else:
+            self.L.orc2_values(t, self.strat.ctypes.data, 3, 1)
+        self.L.orc2_regret_update(t, p, self.algo, self.iter_counter)
+        self.L.orc2_reach(t, self.strat.ctypes.data)
+        self.L.orc2_avg_update(t, p, self.algo, self.iter_counter, self.delay)
+
+    def iteration(self, n=1):
         for _ in range(n):
             for p in (0, 1):  # _CFRBase.py:122-134
-                if self.lean:
-                    self.L.orc2_values(t, self.strat.ctypes.data, 1 << p, 0)
-                else:
-                    self.L.orc2_values(t, self.strat.ctypes.data, 3, 1)
-                self.L.orc2_regret_update(t, p, self.algo, self.iter_counter)
-                self.L.orc2_reach(t, self.strat.ctypes.data)
-                self.L.orc2_avg_update(t, p, self.algo, self.iter_counter, self.delay)
+                self.half_iteration(p)
             self.iter_counter += 1
 
     def _metric(self, expl):

@@ -127,6 +127,8 @@ def lib():
     gp = C.POINTER(PrlBoardGame)
     L.prl_board_layout.argtypes = [C.POINTER(C.c_int32)]
     L.prl_board_grid.argtypes = []
+    L.prl_board_rows.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.prl_board_rows.restype = C.c_int
     L.prl_board_shape_ok.argtypes = [gp]
     L.prl_board_build_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.prl_board_sweep.argtypes = [gp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

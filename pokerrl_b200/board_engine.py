@@ -132,7 +132,6 @@ class BoardCFRSolver:
         torch.cuda.synchronize(dev)
         self.t_prob = torch.from_numpy(np.ascontiguousarray(spec.board_prob[sel], np.float32)).to(dev)
         self.t_mult = torch.from_numpy(np.ascontiguousarray(spec.board_mult[sel], np.float32)).to(dev)
-        # strength-ordered tables: the rows of decision node d (A_d actions) of board j are rows base_d + j * A_d + a
         n_local = st["n_local"]
         dec = [i for i in range(n_local) if st["kind"][i] <= 1]
         self.rows_per_board = sum(st["n_children"][i] for i in dec)
@@ -147,16 +146,18 @@ class BoardCFRSolver:
         # fixed point: |sum| <= n_sym * K * max pot / 2 with headroom; 62 value bits
         bound = max(self.n_sym, 1) * g.eq_const * max(st["pot"]) * 0.5 * 4.0
         g.frac_bits = 62 - int(math.ceil(math.log2(bound)))
+        # board-major rows: everything a (board, seat) unit touches is contiguous - row(i, j) = j * rows_per_board + row_of[i]
+        row_of, rpb = (C.c_int32 * 16)(), C.c_int32(0)
+        nat.call("prl_board_rows", row_of, C.byref(rpb))
+        assert rpb.value == self.rows_per_board
         self.local_rows = {}  # local child node -> (row on board 0, stride per board)
-        base = 0
         for i in range(n_local):
             g.row0[i], g.row_m[i] = -1, 0
         for d in dec:
-            A, fc = st["n_children"][d], st["first_child"][d]
-            for a in range(A):
-                g.row0[fc + a], g.row_m[fc + a] = base + a, A
-                self.local_rows[fc + a] = (base + a, A)
-            base += nb * A
+            for a in range(st["n_children"][d]):
+                c = st["first_child"][d] + a
+                g.row0[c], g.row_m[c] = row_of[c], rpb.value
+                self.local_rows[c] = (int(row_of[c]), rpb.value)
         g.grid = int(grid) if grid else int(nat.lib().prl_board_grid())
         g.tables, g.board_prob, g.board_mult = self.t_blob.data_ptr(), self.t_prob.data_ptr(), self.t_mult.data_ptr()
         g.regret, g.avg = self.regret.data_ptr(), self.avg.data_ptr()

@@ -48,7 +48,7 @@ constexpr int kBlobA = kRecBytes + kShBytes;                // 10 880 B, needed 
 constexpr int kBlobBytes = kBlobA + kRowIdxBytes;           // 15 392 B
 static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-constexpr int kThreads = 448;  // 14 warps; 3 strength positions per thread (2 * 448 + 185)
+constexpr int kThreads = 384;  // 12 warps; 3 strength positions per thread (3 * 384 = 1152 >= 1081: 94 % of the lanes busy)
 constexpr int kPerThread = 3;
 constexpr int kWarps = kThreads / 32;
 
@@ -72,16 +72,22 @@ struct ShapeFHP {
         return n;
     }
     static constexpr int n_sd = 5, n_fold = 4;
-    // index of decision node i among the decision nodes (table row groups)
-    static constexpr int dec_index(int i) {
+    // table rows of one board: the rows of seat 0's decision nodes first, then seat 1's, children in breadth-first order
+    static constexpr int rows_of_seat(int p) {
         int n = 0;
-        for (int k = 0; k < i; ++k) n += (kind(k) <= 1);
+        for (int i = 1; i < N; ++i) n += (kind(parent(i)) == p);
         return n;
     }
-    static constexpr int n_dec = 6;
+    static constexpr int rows = 14;
+    static constexpr int row_of(int c) {  // c = child of a decision node
+        const int p = kind(parent(c));
+        int n = (p == 0) ? 0 : rows_of_seat(0);
+        for (int k = 1; k < c; ++k) n += (kind(parent(k)) == p);
+        return n;
+    }
 };
 static_assert(ShapeFHP::count(4) == ShapeFHP::n_sd && ShapeFHP::count(3) == ShapeFHP::n_fold, "shape");
-static_assert(ShapeFHP::count(0) + ShapeFHP::count(1) == ShapeFHP::n_dec, "shape");
+static_assert(ShapeFHP::rows_of_seat(0) + ShapeFHP::rows_of_seat(1) == ShapeFHP::rows, "shape");
 
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
@@ -107,11 +113,12 @@ constexpr int kErBytes = ((ShapeFHP::n_sd * kErVec * 4) + 15) & ~15;
 constexpr int kBlobOff = kErOff + kErBytes;                                 // 2 x (rec + hand ids)
 constexpr int kRowIdxOff = kBlobOff + 2 * kBlobA;                           // card rows (single buffer)
 constexpr int kCsOff = kRowIdxOff + kRowIdxBytes;                           // float cs[4][48] per-card sums of the fold vectors
-constexpr int kMiscOff = kCsOff + ShapeFHP::n_fold * kRowPad * 4;           // float wsum[5][16], wexc[5][16], tot[5], tf[4]
-constexpr int kMiscBytes = (5 * 16 + 5 * 16 + 8 + 8) * 4;
+constexpr int kCsdOff = kCsOff + ShapeFHP::n_fold * kRowPad * 4;            // double csd[4][48]: the same sums before rounding
+constexpr int kMiscOff = kCsdOff + ShapeFHP::n_fold * kRowPad * 8;          // double wsum[5][16], wexc[5][16]; float tf[8]
+constexpr int kMiscBytes = (5 * 16 + 5 * 16) * 8 + 8 * 4;
 constexpr int kBarOff = kMiscOff + kMiscBytes;                              // 3 mbarriers
 constexpr int kSmemBytes = kBarOff + 32;
-static_assert(kBlobOff % 16 == 0 && kRowIdxOff % 16 == 0 && kBarOff % 8 == 0, "alignment");
+static_assert(kBlobOff % 16 == 0 && kRowIdxOff % 16 == 0 && kCsdOff % 8 == 0 && kMiscOff % 8 == 0 && kBarOff % 8 == 0, "alignment");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 
 struct SweepArgs {
@@ -121,9 +128,10 @@ struct SweepArgs {
     float m_old, m_new;            // CFRPlus.py:68-73
     int src_own, src_opp;          // evaluation: 0 = regret matching of `regret`, 1 = `avg` rows as they are
     double fx_scale;               // 2^frac_bits
+    float sc[16];                  // terminal n: K * pot / 2, negated where the seat of this sweep is the folder
 };
 
-// ---- PTX helpers: mbarrier + 1-D bulk copy global -> shared (TMA), sm_90+
+// ---- PTX helpers: mbarrier + 1-D bulk copy global -> shared (TMA) + bulk L2 prefetch, sm_90+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -135,6 +143,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -163,9 +174,11 @@ __device__ __forceinline__ void node_strategy(const float (&g)[A], int src, floa
         s[a] = fmaxf(g[a], 0.0f);
         sum += s[a];
     }
-    const float inv = (sum > 0.0f) ? 1.0f / sum : 0.0f;
+    const bool pos = sum > 0.0f;
+    const float inv = pos ? __frcp_rn(sum) : 0.0f;  // correctly rounded reciprocal, no slow-path branch
+    const float uni = pos ? 0.0f : 1.0f / (float)A;  // CFRPlus.py:53-58: uniform where no regret is positive
 #pragma unroll
-    for (int a = 0; a < A; ++a) s[a] = (sum > 0.0f) ? s[a] * inv : 1.0f / (float)A;
+    for (int a = 0; a < A; ++a) s[a] = fmaf(s[a], inv, uni);
 }
 
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
@@ -174,6 +187,7 @@ __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 // =====================================================================================================================
 // The sweep kernel.  P = seat whose values are computed; EVAL = false: CFR+ update of seat P (regrets, average);
 // EVAL = true: values and best-response values of seat P under the strategies selected by src_own / src_opp.
+// Table rows of board j: [j][14][1088] floats, rows ShapeFHP::row_of(child); everything a unit touches is contiguous.
 // =====================================================================================================================
 template <class SH, int P, bool EVAL>
 __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArgs a) {
@@ -181,10 +195,10 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     float* S = reinterpret_cast<float*>(smem + kSOff);
     float* Er = reinterpret_cast<float*>(smem + kErOff);
     float* cs = reinterpret_cast<float*>(smem + kCsOff);
-    float* wsum = reinterpret_cast<float*>(smem + kMiscOff);  // [5][16] warp totals of the main scans
-    float* wexc = wsum + 5 * 16;                               // [5][16] exclusive prefix of the warp totals
-    float* tot = wexc + 5 * 16;                                // [8]     totals of the showdown vectors
-    float* tf = tot + 8;                                       // [8]     totals of the fold vectors
+    double* csd = reinterpret_cast<double*>(smem + kCsdOff);
+    double* wsum = reinterpret_cast<double*>(smem + kMiscOff);  // [5][16] warp totals of the main scans
+    double* wexc = wsum + 5 * 16;                                // [5][16] exclusive prefix of the warp totals - total / 2
+    float* tf = reinterpret_cast<float*>(wexc + 5 * 16);         // [8]     totals of the fold vectors
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);  // [0], [1]: blob A buffers; [2]: card rows
     const int16_t* rowidx = reinterpret_cast<const int16_t*>(smem + kRowIdxOff);
 
@@ -193,7 +207,17 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     const int nb = G.n_boards;
     constexpr int OPP = 1 - P;
     constexpr int NSD = SH::n_sd, NF = SH::n_fold;
+    constexpr int ROWS = SH::rows;
+    constexpr int OWN0 = (P == 0) ? 0 : SH::rows_of_seat(0);      // first table row of the seat / of the opponent
+    constexpr int OPP0 = (P == 0) ? SH::rows_of_seat(0) : 0;
+    constexpr int NOWN = SH::rows_of_seat(P), NOPP = SH::rows_of_seat(OPP);
+    constexpr size_t kBoardFloats = (size_t)ROWS * kLdb;
     const unsigned char* blob_g = reinterpret_cast<const unsigned char*>(G.tables);
+    // tables the two seats' strategies come from (evaluation: regret matching of `regret` or the rows of `avg`)
+    const float* tab_opp = (EVAL && a.src_opp == 1) ? G.avg : G.regret;
+    const float* tab_own = (EVAL && a.src_own == 1) ? G.avg : G.regret;
+    const bool do_avg = !EVAL && a.iter >= a.delay;
+    const bool read_avg = do_avg && a.m_old != 0.0f;
 
     // private chance-sum accumulators of this CTA (global, L2-resident): [2][kRange] int64
     long long* wp = reinterpret_cast<long long*>(G.w_private) + (size_t)blockIdx.x * 2 * kRange;
@@ -208,11 +232,18 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     }
     __syncthreads();
     int j = blockIdx.x;
+    // rows of board jj into L2 ahead of their use (one bulk prefetch per contiguous piece; nothing waits on them)
+    auto prefetch_rows = [&](int jj) {
+        bulk_prefetch_l2(tab_opp + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb, NOPP * kLdb * 4);
+        bulk_prefetch_l2(tab_own + (size_t)jj * kBoardFloats + (size_t)OWN0 * kLdb, NOWN * kLdb * 4);
+        if (read_avg) bulk_prefetch_l2(G.avg + (size_t)jj * kBoardFloats + (size_t)OWN0 * kLdb, NOWN * kLdb * 4);
+    };
     if (tid == 0 && j < nb) {  // first board's tables
         mbar_expect_tx(&bars[0], kBlobA);
         bulk_g2s(smem + kBlobOff, blob_g + (size_t)j * kBlobBytes, kBlobA, &bars[0]);
         mbar_expect_tx(&bars[2], kRowIdxBytes);
         bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)j * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
+        prefetch_rows(j);
     }
 
     for (int it = 0; j < nb; j += gridDim.x, ++it) {
@@ -221,64 +252,86 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         const uint64_t* rec = reinterpret_cast<const uint64_t*>(blob);
         const int16_t* sh = reinterpret_cast<const int16_t*>(blob + kRecBytes);
         const int jn = j + gridDim.x;
-        if (tid == 0 && jn < nb) {  // next board's records + hand ids into the other buffer (free since the last barrier)
+        if (tid == 0 && jn < nb) {  // next board: records + hand ids into the other buffer (free since the last barrier), rows into L2
             mbar_expect_tx(&bars[buf ^ 1], kBlobA);
             bulk_g2s(smem + kBlobOff + (buf ^ 1) * kBlobA, blob_g + (size_t)jn * kBlobBytes, kBlobA, &bars[buf ^ 1]);
+            prefetch_rows(jn);
         }
         const float prob = __ldg(G.board_prob + j);
+        const float* opp_rows = tab_opp + (size_t)j * kBoardFloats + (size_t)OPP0 * kLdb + tid;
         mbar_wait(&bars[buf], (it >> 1) & 1);
 
         // ------------------------------------------------------------------------------------------ P1: reach, top-down
-        // x[i] = reach of the OPPONENT at local node i (StrategyFiller.py:118-146); terminal rows go to S in strength order
-#pragma unroll 1
-        for (int k = 0; k < kPerThread; ++k) {
-            const int i = tid + k * kThreads;
-            if (i >= kLive) break;
-            const int hand = sh[i];
-            float x[SH::N];
-            x[0] = __ldg(a.trunk_reach_opp + hand) * prob;  // the deal (StrategyFiller.py:137-140); blocked hands are not stored
-            static_for<0, SH::N>([&](auto I) {
-                constexpr int n = decltype(I)::value;
-                constexpr int A = SH::n_children(n);
-                if constexpr (SH::kind(n) <= 1) {
-                    constexpr int fc = SH::first_child(n);
-                    if constexpr (SH::kind(n) == OPP) {
-                        const float* tab = (EVAL && a.src_opp == 1) ? G.avg : G.regret;
-                        const float* row = tab + ((size_t)G.row0[fc] + (size_t)j * A) * kLdb + i;
-                        float g[A], s[A];
+        // x[i] = reach of the OPPONENT at local node i (StrategyFiller.py:118-146); terminal rows go to S in strength order.
+        // All loads of the thread's three strength positions are in flight together.
+        {
+            float g[kPerThread][NOPP], x0[kPerThread];
 #pragma unroll
-                        for (int c = 0; c < A; ++c) g[c] = ld_stream(row + (size_t)c * kLdb);
-                        node_strategy<A>(g, EVAL ? a.src_opp : 0, s);
+            for (int k = 0; k < kPerThread; ++k) {
+                const int i = tid + k * kThreads;
+                if (i < kLive) {
 #pragma unroll
-                        for (int c = 0; c < A; ++c) x[fc + c] = x[n] * s[c];
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < A; ++c) x[fc + c] = x[n];
-                    }
-                } else if constexpr (SH::kind(n) == 4) {
-                    S[SH::vec_index(n) * kLdb + i] = x[n];
-                } else {
-                    S[(NSD + SH::vec_index(n)) * kLdb + i] = x[n];
+                    for (int r = 0; r < NOPP; ++r) g[k][r] = ld_stream(opp_rows + (size_t)r * kLdb + k * kThreads);
+                    x0[k] = __ldg(a.trunk_reach_opp + sh[i]);
                 }
-            });
+            }
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) {
+                const int i = tid + k * kThreads;
+                if (i < kLive) {
+                    float x[SH::N];
+                    x[0] = x0[k] * prob;  // the deal (StrategyFiller.py:137-140); blocked hands are not stored at all
+                    static_for<0, SH::N>([&](auto I) {
+                        constexpr int n = decltype(I)::value;
+                        constexpr int A = SH::n_children(n);
+                        if constexpr (SH::kind(n) <= 1) {
+                            constexpr int fc = SH::first_child(n);
+                            if constexpr (SH::kind(n) == OPP) {
+                                float gg[A], s[A];
+#pragma unroll
+                                for (int c = 0; c < A; ++c) gg[c] = g[k][SH::row_of(fc + c) - OPP0];
+                                node_strategy<A>(gg, EVAL ? a.src_opp : 0, s);
+#pragma unroll
+                                for (int c = 0; c < A; ++c) x[fc + c] = x[n] * s[c];
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < A; ++c) x[fc + c] = x[n];
+                            }
+                        } else if constexpr (SH::kind(n) == 4) {
+                            S[SH::vec_index(n) * kLdb + i] = x[n];
+                        } else {
+                            S[(NSD + SH::vec_index(n)) * kLdb + i] = x[n];
+                        }
+                    });
+                }
+            }
         }
         __syncthreads();  // B1: S complete
 
         // ------------------------------------------------------------------------------------------ P2a: card rows
         // quad (live card lc, lane q): entries [12 q, 12 q + 12) of the card's row in strength order.  Showdown vectors:
         // centred exclusive prefix sums Er[v][lc][k] = (mass of the k weakest hands holding the card) - half the row's mass;
-        // fold vectors: the row's mass cs[f][lc].
+        // fold vectors: the row's mass cs[f][lc].  Two groups of 47 quads share the nine vectors (SD 0-2 + fold 0-1 | SD 3-4 +
+        // fold 2-3); the other threads start on the main scans, which only read S as well.
         mbar_wait(&bars[2], it & 1);
-        if (tid < kLiveCards * 4) {
-            const int lc = tid >> 2, q = tid & 3;
+        float a0[NSD], a1[NSD], a2[NSD];
+        double pre[NSD];
+        constexpr int kQuadThreads = kLiveCards * 4;  // 188
+        if (warp < (2 * kQuadThreads + 31) / 32) {   // whole warps (the quad shuffles name every lane)
+            const int grp = (tid >= kQuadThreads) ? 1 : 0;
+            const int t = tid - grp * kQuadThreads;
+            const bool row_live = t < kQuadThreads;
+            const int lc = row_live ? (t >> 2) : (kLiveCards - 1), q = tid & 3;
+            const unsigned qmask = 0xFu << (lane & 28);  // the two groups run different trip counts: shuffles name the quad only
             const uint2* rp = reinterpret_cast<const uint2*>(rowidx + lc * kRowPad + q * kRowSeg);
             const uint2 w0 = rp[0], w1 = rp[1], w2 = rp[2];
             const unsigned pk[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
             int idx[kRowSeg];
 #pragma unroll
             for (int e = 0; e < kRowSeg; ++e) idx[e] = (pk[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+            const int v_lo = grp ? 3 : 0, v_hi = grp ? NSD : 3;
 #pragma unroll 1
-            for (int v = 0; v < NSD; ++v) {
+            for (int v = v_lo; v < v_hi; ++v) {
                 const float* Sv = S + v * kLdb;
                 float inc[kRowSeg];
                 float run = 0.0f;
@@ -288,38 +341,32 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                     run += Sv[idx[e]];
                 }
                 float sc = run;  // inclusive scan over the quad
-                float t = __shfl_up_sync(0xffffffffu, sc, 1, 4);
-                if (q >= 1) sc += t;
-                t = __shfl_up_sync(0xffffffffu, sc, 2, 4);
-                if (q >= 2) sc += t;
-                const float half = 0.5f * __shfl_sync(0xffffffffu, sc, 3, 4);
+                float tt = __shfl_up_sync(qmask, sc, 1, 4);
+                if (q >= 1) sc += tt;
+                tt = __shfl_up_sync(qmask, sc, 2, 4);
+                if (q >= 2) sc += tt;
+                const float half = 0.5f * __shfl_sync(qmask, sc, 3, 4);
                 const float off = (sc - run) - half;
                 float* row = Er + v * kErVec + lc * kErStride + q * kRowSeg;
 #pragma unroll
                 for (int e = 0; e < kRowSeg; ++e)
-                    if (q * kRowSeg + e < kErStride) row[e] = off + inc[e];
+                    if (row_live && q * kRowSeg + e < kErStride) row[e] = off + inc[e];
             }
 #pragma unroll 1
-            for (int f = 0; f < NF; ++f) {
+            for (int f = 2 * grp; f < 2 * grp + 2; ++f) {
                 const float* Sv = S + (NSD + f) * kLdb;
-                float run = 0.0f;
+                double run = 0.0;  // double: the fold value subtracts these sums from the total (cancellation)
 #pragma unroll
-                for (int e = 0; e < kRowSeg; ++e) run += Sv[idx[e]];
-                run += __shfl_xor_sync(0xffffffffu, run, 1, 4);
-                run += __shfl_xor_sync(0xffffffffu, run, 2, 4);
-                if (q == 0) cs[f * kRowPad + lc] = run;
+                for (int e = 0; e < kRowSeg; ++e) run += (double)Sv[idx[e]];
+                run += __shfl_xor_sync(qmask, run, 1, 4);
+                run += __shfl_xor_sync(qmask, run, 2, 4);
+                if (row_live && q == 0) csd[f * kRowPad + lc] = run;
             }
         }
-        __syncthreads();  // B2: card rows done, S may be overwritten, the row table may be replaced
-        if (tid == 0 && jn < nb) {
-            mbar_expect_tx(&bars[2], kRowIdxBytes);
-            bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)jn * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
-        }
-
-        // ------------------------------------------------------------------------------------------ P2b: main scans
-        // centred exclusive prefix sums over the strength order, in place: E[k] = (mass of the k weakest hands) - total / 2,
-        // k = 0 .. 1081.  Thread t owns positions 3t .. 3t+2; double accumulation inside a thread and across warps.
-        float a0[NSD], a1[NSD], a2[NSD], pre[NSD];
+        __syncwarp();
+        // ------------------------------------------------------------------------------------------ P2b: main scans, part 1
+        // centred exclusive prefix sums over the strength order: E[k] = (mass of the k weakest hands) - total / 2, k = 0 ..
+        // 1081.  Thread t owns positions 3t .. 3t+2; sums in double (the showdown value is a difference of two prefixes).
         {
             const int b0 = 3 * tid;
 #pragma unroll
@@ -328,54 +375,60 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 a0[v] = (b0 < kLive) ? Sv[b0] : 0.0f;
                 a1[v] = (b0 + 1 < kLive) ? Sv[b0 + 1] : 0.0f;
                 a2[v] = (b0 + 2 < kLive) ? Sv[b0 + 2] : 0.0f;
-                const float loc = (a0[v] + a1[v]) + a2[v];
-                float incw = loc;
+                const double loc = ((double)a0[v] + (double)a1[v]) + (double)a2[v];
+                double incw = loc;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const float t = __shfl_up_sync(0xffffffffu, incw, o);
-                    if (lane >= o) incw += t;
+                    const double tt = __shfl_up_sync(0xffffffffu, incw, o);
+                    if (lane >= o) incw += tt;
                 }
                 pre[v] = incw - loc;  // exclusive within the warp
                 if (lane == 31) wsum[v * 16 + warp] = incw;
             }
         }
-        __syncthreads();  // B3
+        __syncthreads();  // B2: card rows done, S may be overwritten, the row table may be replaced
+        if (tid == 0 && jn < nb) {
+            mbar_expect_tx(&bars[2], kRowIdxBytes);
+            bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)jn * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
+        }
         if (warp == 0) {
 #pragma unroll
-            for (int v = 0; v < NSD; ++v) {  // exclusive scan of the 14 warp totals (double: 14 terms of a large sum)
-                const double w = (lane < kWarps) ? (double)wsum[v * 16 + lane] : 0.0;
+            for (int v = 0; v < NSD; ++v) {  // exclusive scan of the 14 warp totals
+                const double w = (lane < kWarps) ? wsum[v * 16 + lane] : 0.0;
                 double sc = w;
 #pragma unroll
                 for (int o = 1; o < 16; o <<= 1) {
-                    const double t = __shfl_up_sync(0xffffffffu, sc, o);
-                    if (lane >= o) sc += t;
+                    const double tt = __shfl_up_sync(0xffffffffu, sc, o);
+                    if (lane >= o) sc += tt;
                 }
                 const double total = __shfl_sync(0xffffffffu, sc, kWarps - 1);
-                if (lane < kWarps) wexc[v * 16 + lane] = (float)((sc - w) - 0.5 * total);
-                if (lane == 0) tot[v] = (float)total;
+                if (lane < kWarps) wexc[v * 16 + lane] = (sc - w) - 0.5 * total;
             }
         } else if (warp == 1) {
 #pragma unroll
             for (int f = 0; f < NF; ++f) {  // total of a fold vector = half the sum of its card rows
-                float s2 = ((lane < kLiveCards) ? cs[f * kRowPad + lane] : 0.0f) +
-                           ((lane + 32 < kLiveCards) ? cs[f * kRowPad + lane + 32] : 0.0f);
+                const double c0 = (lane < kLiveCards) ? csd[f * kRowPad + lane] : 0.0;
+                const double c1 = (lane + 32 < kLiveCards) ? csd[f * kRowPad + lane + 32] : 0.0;
+                double s2 = c0 + c1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                if (lane == 0) tf[f] = 0.5f * s2;
+                if (lane == 0) tf[f] = (float)(0.5 * s2);
+                if (lane < kLiveCards) cs[f * kRowPad + lane] = (float)c0;  // float copies for the per-hand epilogue
+                if (lane + 32 < kLiveCards) cs[f * kRowPad + lane + 32] = (float)c1;
             }
         }
-        __syncthreads();  // B3b
+        __syncthreads();  // B3
         {
             const int b0 = 3 * tid;
 #pragma unroll
             for (int v = 0; v < NSD; ++v) {
                 float* Sv = S + v * kLdb;
-                float run = pre[v] + wexc[v * 16 + warp];
-                if (b0 <= kLive) Sv[b0] = run;
-                run += a0[v];
-                if (b0 + 1 <= kLive) Sv[b0 + 1] = run;
-                run += a1[v];
-                if (b0 + 2 <= kLive) Sv[b0 + 2] = run;
+                double run = pre[v] + wexc[v * 16 + warp];
+                if (b0 <= kLive) Sv[b0] = (float)run;
+                run += (double)a0[v];
+                if (b0 + 1 <= kLive) Sv[b0 + 1] = (float)run;
+                run += (double)a1[v];
+                if (b0 + 2 <= kLive) Sv[b0 + 2] = (float)run;
             }
         }
         __syncthreads();  // B4: prefix arrays complete
@@ -383,20 +436,34 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // ------------------------------------------------------------------------------------------ P3: values, bottom-up
         const float mult = __ldg(G.board_mult + j);
         const double fx = (double)mult * a.fx_scale;
+        const float* own_rows = tab_own + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
+        float* reg_rows = G.regret + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
+        float* avg_rows = G.avg + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
 #pragma unroll 1
         for (int k = 0; k < kPerThread; ++k) {
             const int i = tid + k * kThreads;
             if (i >= kLive) break;
+            // the seat's rows for this hand, requested before the shared-memory work below
+            float gown[NOWN], av[NOWN];
+#pragma unroll
+            for (int r = 0; r < NOWN; ++r) gown[r] = ld_stream(own_rows + (size_t)r * kLdb + k * kThreads);
+            if (read_avg) {
+#pragma unroll
+                for (int r = 0; r < NOWN; ++r) av[r] = ld_stream(avg_rows + (size_t)r * kLdb + k * kThreads);
+            } else {
+#pragma unroll
+                for (int r = 0; r < NOWN; ++r) av[r] = 0.0f;
+            }
             const uint64_t w = rec[i];
+            const int hand = sh[i];
+            long long* wacc = wp + hand;
+            const long long w_ev = *wacc;
+            long long w_br = 0;
+            if constexpr (EVAL) w_br = wacc[kRange];
             const int gs = (int)(w & 0x7ffu), ge = (int)((w >> 11) & 0x7ffu);
             const int lc1 = (int)((w >> 22) & 0x3fu), lc2 = (int)((w >> 28) & 0x3fu);
             const int o1 = lc1 * kErStride + (int)((w >> 34) & 0x3fu), o1e = o1 + (int)((w >> 40) & 0x3fu);
             const int o2 = lc2 * kErStride + (int)((w >> 46) & 0x3fu), o2e = o2 + (int)((w >> 52) & 0x3fu);
-            const int hand = sh[i];
-            long long* wacc = wp + hand;
-            const long long w_ev = *wacc;  // requested early, consumed at the end
-            long long w_br = 0;
-            if constexpr (EVAL) w_br = wacc[kRange];
             float e[SH::N], br[EVAL ? SH::N : 1];
             // terminal rows (ValueFiller.py:103-158): ev = equity * K * pot / 2, the folder loses
             static_for<0, SH::N>([&](auto I) {
@@ -407,13 +474,12 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                     const float* Rv = Er + v * kErVec;
                     const float all = Ev[gs] + Ev[ge];
                     const float rows = (Rv[o1] + Rv[o1e]) + (Rv[o2] + Rv[o2e]);
-                    e[n] = (all - rows) * (G.eq_const * G.pot[n] * 0.5f);
+                    e[n] = (all - rows) * a.sc[n];
                     if constexpr (EVAL) br[n] = e[n];
                 } else if constexpr (SH::kind(n) == 3) {
                     constexpr int f = SH::vec_index(n);
                     const float mass = ((tf[f] - cs[f * kRowPad + lc1]) - cs[f * kRowPad + lc2]) + S[(NSD + f) * kLdb + i];
-                    const float sc = G.eq_const * G.pot[n] * 0.5f;
-                    e[n] = mass * ((G.acted_last[n] == P) ? -sc : sc);
+                    e[n] = mass * a.sc[n];
                     if constexpr (EVAL) br[n] = e[n];
                 }
             });
@@ -435,47 +501,30 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                             br[n] = b;
                         }
                     } else {
-                        const size_t r0 = ((size_t)G.row0[fc] + (size_t)j * A) * kLdb + i;
+                        constexpr int r0 = SH::row_of(fc) - OWN0;  // rows r0 .. r0 + A - 1 of the seat's block
                         float g[A], s[A];
+#pragma unroll
+                        for (int c = 0; c < A; ++c) g[c] = gown[r0 + c];
+                        node_strategy<A>(g, EVAL ? a.src_own : 0, s);
+                        float v = s[0] * e[fc];
+#pragma unroll
+                        for (int c = 1; c < A; ++c) v += s[c] * e[fc + c];
+                        e[n] = v;
                         if constexpr (EVAL) {
-                            const float* tab = (a.src_own == 1) ? G.avg : G.regret;
+                            float b = br[fc];
 #pragma unroll
-                            for (int c = 0; c < A; ++c) g[c] = ld_stream(tab + r0 + (size_t)c * kLdb);
-                            node_strategy<A>(g, a.src_own, s);
-                            float v = s[0] * e[fc], b = br[fc];
-#pragma unroll
-                            for (int c = 1; c < A; ++c) {
-                                v += s[c] * e[fc + c];
-                                b = fmaxf(b, br[fc + c]);
-                            }
-                            e[n] = v;
+                            for (int c = 1; c < A; ++c) b = fmaxf(b, br[fc + c]);
                             br[n] = b;
                         } else {
-                            float av[A];
-#pragma unroll
-                            for (int c = 0; c < A; ++c) g[c] = ld_stream(G.regret + r0 + (size_t)c * kLdb);
-                            const bool do_avg = a.iter >= a.delay;
-                            if (do_avg && a.m_old != 0.0f) {
-#pragma unroll
-                                for (int c = 0; c < A; ++c) av[c] = ld_stream(G.avg + r0 + (size_t)c * kLdb);
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < A; ++c) av[c] = 0.0f;
-                            }
-                            node_strategy<A>(g, 0, s);
-                            float v = s[0] * e[fc];
-#pragma unroll
-                            for (int c = 1; c < A; ++c) v += s[c] * e[fc + c];
-                            e[n] = v;
 #pragma unroll
                             for (int c = 0; c < A; ++c) g[c] = fmaxf((e[fc + c] - v) + g[c], 0.0f);  // CFRPlus.py:37-41
                             node_strategy<A>(g, 0, s);
 #pragma unroll
-                            for (int c = 0; c < A; ++c) st_stream(G.regret + r0 + (size_t)c * kLdb, g[c]);
+                            for (int c = 0; c < A; ++c) st_stream(reg_rows + (size_t)(r0 + c) * kLdb + k * kThreads, g[c]);
                             if (do_avg) {  // CFRPlus.py:65-87 (not reach-weighted)
 #pragma unroll
                                 for (int c = 0; c < A; ++c)
-                                    st_stream(G.avg + r0 + (size_t)c * kLdb, a.m_old * av[c] + a.m_new * s[c]);
+                                    st_stream(avg_rows + (size_t)(r0 + c) * kLdb + k * kThreads, a.m_old * av[r0 + c] + a.m_new * s[c]);
                             }
                         }
                     }
@@ -617,6 +666,13 @@ bool shape_matches(const prl_board_game_t* g) {
     return true;
 }
 
+// the table layout the kernel compiles in: row(i, j) = j * 14 + row_of(i)
+bool layout_matches(const prl_board_game_t* g) {
+    for (int i = 1; i < ShapeFHP::N; ++i)
+        if (g->row0[i] != ShapeFHP::row_of(i) || g->row_m[i] != ShapeFHP::rows) return false;
+    return true;
+}
+
 int default_grid() {
     static int cached[64] = {0};
     int dev = 0;
@@ -656,6 +712,12 @@ extern "C" int prl_board_layout(int32_t* out) {
 
 extern "C" int prl_board_grid(void) { return default_grid(); }
 
+extern "C" int prl_board_rows(int32_t* row_of, int32_t* rows_per_board) {
+    for (int i = 0; i < 16; ++i) row_of[i] = (i >= 1 && i < ShapeFHP::N) ? ShapeFHP::row_of(i) : -1;
+    *rows_per_board = ShapeFHP::rows;
+    return 0;
+}
+
 extern "C" int prl_board_shape_ok(const prl_board_game_t* g) { return (g && shape_matches(g)) ? 1 : 0; }
 
 extern "C" int prl_board_build_tables(const int32_t* ranks, const uint64_t* board_mask, const int8_t* hand_cards, int n_boards,
@@ -670,6 +732,7 @@ extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int s
                                int iter, int delay, prl_stream_t stream) {
     if (!g || !shape_matches(g)) return prl::fail("prl_board_sweep: the post-deal subtree does not have the compiled shape");
     if (g->n_range != kRange || g->n_deck != kDeck) return prl::fail("prl_board_sweep: 52-card deck / 1326 hands only");
+    if (!layout_matches(g)) return prl::fail("prl_board_sweep: row0 / row_m must be the board-major layout of prl_board_rows");
     if (p < 0 || p > 1) return prl::fail("prl_board_sweep: bad seat");
     if (!g->tables || !g->regret || !g->avg || !g->w_private || !g->w_total || !trunk_reach_opp)
         return prl::fail("prl_board_sweep: missing buffers");
@@ -687,6 +750,10 @@ extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int s
     a.src_own = src_own;
     a.src_opp = src_opp;
     a.fx_scale = (double)(1ull << g->frac_bits);
+    for (int n = 0; n < 16; ++n) {
+        const bool folder = n < g->n_local && g->kind[n] == PRL_KIND_FOLD && g->acted_last[n] == p;
+        a.sc[n] = (n < g->n_local) ? g->eq_const * g->pot[n] * 0.5f * (folder ? -1.0f : 1.0f) : 0.0f;
+    }
     if (int e = prl::check(cudaMemsetAsync(g->w_total, 0, sizeof(long long) * 2 * kRange, s), "prl_board_sweep: memset")) return e;
     int rc;
     if (eval) rc = (p == 0) ? launch_sweep<0, true>(a, grid, s) : launch_sweep<1, true>(a, grid, s);
