@@ -8,7 +8,7 @@ tree, with the exact best-response evaluation of the current AND the average str
 
 Default workload `fhp` (BASELINE.json configs[2], the game the metric is quoted on): Flop5Holdem (PokerRL/game/games.py:
 222-254) - full game, all C(52,5) = 2 598 960 boards as 134 459 suit-isomorphism classes, 1326-hand ranges, 2 016 890
-public nodes, 1 882 430 table rows; ~110 GB of HBM on one B200.  `leduc_b5` (configs[1]) = DiscretizedNLLeduc with
+public nodes, 1 882 430 table rows, run by the board-resident engine (pokerrl_b200/board_engine.py: 17 GB of HBM).  `leduc_b5` (configs[1]) = DiscretizedNLLeduc with
 bet_sets.B_5 (873 586 nodes, range 6).  The trees are deterministic: no dataset, no seed.
 
 N > 1 (torchrun): fhp shards the boards over the ranks (strong scaling, one NCCL all-reduce of the chance-node sums per
@@ -16,8 +16,10 @@ bottom-up sweep, pokerrl_b200/distributed.py); the Leduc workloads run one indep
 `starting_stack_sizes` axis, weak scaling, no data-path collective).
 
 Rank 0 prints ONE JSON line.  `--impl reference` times the CPU restatement of the reference's path on the host cores
-(/root/reference does not exist on the GPU box): the C oracle (OpenMP) for Leduc; for fhp - a game the reference cannot
-run at all (SURVEY.md headline 2) - the float64 numpy oracle on a bounded board sample, scaled to the full board count.
+(/root/reference does not exist on the GPU box): the C oracles (OpenMP, all host threads) - oracle/cfr_oracle.c for Leduc;
+for fhp, a game the reference cannot run at all (SURVEY.md headline 2), oracle/cfr2_oracle.c (float64, the same O(R)
+showdown algorithm class as the GPU) on the first FHP_CPU_BOARDS board classes, a whole fixed instance that the GPU arm
+also reports as a matched pair; the full-game figure is that instance scaled by the board count (cost is per board).
 """
 import argparse
 import contextlib
@@ -145,26 +147,32 @@ def run_cpu_leduc(ft, n_iters, eval_every, threads):
     return (time.perf_counter() - t0) / n_iters, s.n_threads
 
 
-def run_cpu_fhp(n_boards_sample, n_iters, n_boards_full):
-    """float64 numpy oracle (oracle/cfr2_numpy.py) on a sample of boards; returns (seconds per FULL-GAME iteration
-    extrapolated linearly in the number of boards, seconds per sampled iteration, boards sampled, BLAS threads)."""
-    import cfr2_numpy as o2
-    from twocard_common import fhp_tree, oracle_tree, random_board_spec
-    ft = fhp_tree(random_board_spec(n_boards_sample, 123))
-    nb = ft.board_spec.boards.shape[0]
-    c = o2.Oracle2CFR(oracle_tree(ft), "CFRPlus", ev_normalizer=ft.game_cls.EV_NORMALIZER)
-    c.iteration()  # builds and caches the per-board sign matrices (one-off in a real solver as well)
+FHP_CPU_BOARDS = 2048  # matched CPU / GPU instance: the first 2048 suit-isomorphism classes
+
+
+def fhp_subset(spec, n):
+    from pokerrl_b200.game.holdem_boards import BoardSpec
+    return BoardSpec(spec.boards[:n], spec.board_prob[:n], spec.board_mult[:n], spec.sym_perm, "first %d classes" % n)
+
+
+def run_cpu_fhp(n_boards, n_iters, threads):
+    """oracle/cfr2_oracle.c (float64, OpenMP) CFR+ on the first n_boards classes, lean schedule (what a CFR half-iteration
+    needs, i.e. the GPU's schedule).  Returns (seconds per iteration on this instance, threads, exploitability mbb/g)."""
+    import numpy as np
+    import cfr2_c
+    from twocard_common import fhp_tree, oracle_ranks
+    from pokerrl_b200.game.games import FlopHoldemRules
+    from pokerrl_b200.game.holdem_boards import BoardSpec
+    ft = fhp_tree(fhp_subset(BoardSpec.full_game(FlopHoldemRules), n_boards))
+    bc = ft.board_cards()
+    ranks = np.full((bc.shape[0], ft.R), -1, np.int32)
+    ranks[1:] = oracle_ranks(bc[1:])
+    c = cfr2_c.Oracle2CSolver(ft, ranks, "CFRPlus", n_threads=threads, lean=True)
+    c.iteration(1)
     t0 = time.perf_counter()
-    for _ in range(n_iters):
-        c.iteration()
+    c.iteration(n_iters)
     sec = (time.perf_counter() - t0) / n_iters
-    threads = 1
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    except Exception:
-        pass
-    return sec * n_boards_full / nb, sec, nb, threads
+    return sec, c.n_threads, c.exploitability_current()
 
 
 def run_aux(a):
@@ -266,6 +274,268 @@ def run_aux(a):
     print(json.dumps(out))
 
 
+def main_fhp(a, rank, world, local_rank):
+    """BASELINE.json configs[2] (the game the metric is quoted on): Flop5Holdem CFR+ by the board-resident engine."""
+    N_CLASSES = 134459
+    K = a.steps if a.steps is not None else 200
+    W = max(3, a.warmup if a.warmup is not None else 5)
+    nb_used = a.fhp_boards or N_CLASSES
+    cfg = {"workload": "Flop5Holdem CFR+ delay 0, full game: 134 459 suit-isomorphism classes of the 2 598 960 five-card boards, "
+                       "range 1326, stack 20000, exact BR (current+average) every %d iterations%s"
+                       % (a.eval_every, " [DEBUG SUBSET: first %d classes]" % a.fhp_boards if a.fhp_boards else "")}
+    ncpu = os.cpu_count() or 1
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        n_it = max(2, min(K, 8))
+        sec, threads, expl = run_cpu_fhp(FHP_CPU_BOARDS, n_it, ncpu)
+        v = 1.0 / (sec * nb_used / FHP_CPU_BOARDS)
+        sample = ("%d CFR+ iterations of oracle/cfr2_oracle.c (float64, OpenMP, %d threads, the GPU's schedule) on the first %d "
+                  "board classes: %.4f s/iteration = %.3f it/s on that instance; scaled by the board count (%d / %d; cost is per "
+                  "board) to the full game.  The reference itself cannot run Hold'em trees (SURVEY.md headline 2)"
+                  % (n_it, threads, FHP_CPU_BOARDS, sec, 1.0 / sec, nb_used, FHP_CPU_BOARDS))
+        print(json.dumps({
+            "impl": "reference", "metric": "CFR+ iterations/s", "value": v, "unit": "iterations/s", "n_gpus": a.gpus, "steps": n_it,
+            "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (deterministic game tree, no dataset)", "config": cfg,
+            "matched_instance": {"boards": FHP_CPU_BOARDS, "iterations_per_s": 1.0 / sec, "exploitability_mbb_per_g": expl},
+            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pokerrl_b200 import _native as nat
+    from pokerrl_b200.board_engine import BoardCFRSolver
+    from pokerrl_b200.game.holdem_boards import BoardSpec
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = "cuda:%d" % local_rank
+    g, args = fhp_args()
+    t0 = time.perf_counter()
+    spec = BoardSpec.full_game(g.RULES)
+    if a.fhp_boards:
+        spec = fhp_subset(spec, a.fhp_boards)
+    t_spec = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    s = BoardCFRSolver(g, args, spec, device=dev, rank=rank, world=world)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    L = s.L
+
+    def steps(solver, i0, n):
+        out, i = [], i0
+        while i < i0 + n:
+            m = min(a.eval_every - (i % a.eval_every), i0 + n - i)
+            solver.iteration(m)
+            i += m
+            if i % a.eval_every == 0:
+                out.append((i, solver.exploitability_current(), solver.exploitability_average()))
+        return out
+
+    steps(s, 0, W)
+    s.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.5)
+    steps(s, 0, W)
+    s.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0, n_ar0 = nat.lib().prl_launch_count(), s.n_allreduce
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    ev0.record()
+    trace = steps(s, 0, K)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = nat.lib().prl_launch_count() - launches0
+    n_allreduce = s.n_allreduce - n_ar0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+
+    # --- roofline of the dominant kernel (board_sweep_kernel, update form), CUDA events on its stream around each launch
+    def ev_pair():
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    sw, half, evals = [], [], []
+    for rep in range(5):
+        for p in (0, 1):
+            e0, e1 = ev_pair()
+            e0.record()
+            s._sweep_begin(s.bufs, p, False, 0, 0)
+            e1.record()
+            torch.cuda.synchronize()
+            sw.append(e0.elapsed_time(e1))
+    for rep in range(4):  # whole half-iterations (sweep + cross-rank sum + trunk chain)
+        for p in (0, 1):
+            e0, e1 = ev_pair()
+            e0.record()
+            s._update_begin(p)
+            s._update_end(p)
+            e1.record()
+            torch.cuda.synchronize()
+            half.append(e0.elapsed_time(e1))
+        s.iter_counter += 1
+    for rep in range(2):
+        e0, e1 = ev_pair()
+        e0.record()
+        s.exploitability_current()
+        s.exploitability_average()
+        e1.record()
+        torch.cuda.synchronize()
+        evals.append(e0.elapsed_time(e1))
+    sweep_ms, half_ms, eval_ms = statistics.median(sw), statistics.median(half), statistics.median(evals)
+    rows_bytes = L["ldb"] * 4
+    # algorithmic bytes of ONE update launch (DESIGN.md §6): per board 7 opponent regret rows read, 7 own regret rows read +
+    # written, 7 own average rows read + written (35 rows of 1088 floats) + the board's 15 392-byte index tables, once
+    per_board = 35 * rows_bytes + L["blob"]
+    bytes_launch = s.n_boards * per_board
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_launch / (sweep_ms * 1e-3) / 1e9
+    traffic, traffic_note = None, "no ncu capture recorded under profiles/"
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_fhp_sweep_traffic.json")))
+        traffic = tr["dram_bytes_per_board"] * s.n_boards
+        traffic_note = tr["note"]
+    except Exception:
+        pass
+    it_ms = max_ms / K
+    # SURVEY.md §8(d): B_min = 16 R sum(A) + 4 R n_boards per iteration with R = 1326 (regret + average read and written once)
+    b_min = (16 * 1326 * 14 + 4 * 1326) * (N_CLASSES if not a.fhp_boards else a.fhp_boards)
+    roofline = {
+        "bound": "hbm", "kernel": "board_sweep_kernel<ShapeFHP, seat, update> (persistent, 2 CTAs per SM, one (board, seat) unit at a "
+                                  "time; 2 launches per iteration = %.0f %% of the iteration)" % (100 * 2 * sweep_ms / (2 * half_ms)),
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+        "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": sweep_ms, "traffic": traffic, "traffic_note": traffic_note,
+        "bytes_per_board": {"rows": 35 * rows_bytes, "index_tables": L["blob"]},
+        "frac_vs_Bmin": {"B_min_bytes_per_iteration": b_min * (1.0 / world if world > 1 else 1.0),
+                         "achieved_GBps": b_min / world / (2 * half_ms * 1e-3) / 1e9,
+                         "frac": b_min / world / (2 * half_ms * 1e-3) / 1e9 / peak,
+                         "note": "SURVEY.md §8(d) minimum with R = 1326 over a plain iteration (2 half-iterations, no BR pass)"},
+        "time_shares_ms": {"update_sweep_per_seat": sweep_ms, "half_iteration": half_ms,
+                           "trunk_and_cross_rank_sum_per_half_iteration": half_ms - sweep_ms,
+                           "exploitability_current_plus_average": eval_ms, "timed_step_avg": it_ms},
+    }
+
+    # --- matched CPU / GPU instance + shard-invariance proof (small engines on this rank's GPU)
+    matched = None
+    if rank == 0:
+        small = BoardCFRSolver(g, args, fhp_subset(BoardSpec.full_game(g.RULES), FHP_CPU_BOARDS), device=dev)
+        small.iteration(3)
+        torch.cuda.synchronize()
+        e0, e1 = ev_pair()
+        e0.record()
+        small.iteration(20)
+        e1.record()
+        torch.cuda.synchronize()
+        matched = {"boards": FHP_CPU_BOARDS, "gpu_iterations_per_s": 20e3 / e0.elapsed_time(e1)}
+        del small
+    invariance = None
+    if world > 1:
+        sub = fhp_subset(BoardSpec.full_game(g.RULES), 1024)
+        part = BoardCFRSolver(g, args, sub, device=dev, rank=rank, world=world)
+        part.iteration(5)
+        mine = [part.exploitability_current(), part.exploitability_average()]
+        chk = part.bufs.regret.double().sum().item()
+        if rank == 0:
+            one = BoardCFRSolver(g, args, sub, device=dev)
+            one.iteration(5)
+            ref = [one.exploitability_current(), one.exploitability_average()]
+            invariance = {"boards": 1024, "iterations": 5, "sharded": mine, "single_rank_replay": ref,
+                          "max_abs_diff": max(abs(x - y) for x, y in zip(mine, ref)),
+                          "trunk_regret_checksum_equal": chk == one.bufs.regret.double().sum().item()}
+            del one
+        del part
+
+    # --- e2e: the user-facing call (CFRPlus facade: iteration() + logging through ChiefBase, results read on the host)
+    from pokerrl_b200.cfr.CFRPlus import CFRPlus
+    from pokerrl_b200.game import games
+    from pokerrl_b200.rl.base_cls.workers.ChiefBase import ChiefBase
+    del s
+    torch.cuda.empty_cache()
+    chief = ChiefBase(t_prof=None)
+    with contextlib.redirect_stdout(io.StringIO()):
+        cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=games.Flop5Holdem, agent_bet_set=[1.0], delay=0,
+                      eval_every=a.eval_every, device=dev, board_spec=spec)
+    for _ in range(W):
+        cfr.iteration()
+    cfr.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0t = time.perf_counter()
+    for _ in range(K):
+        cfr.iteration()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0t
+    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_s = float(t2.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {
+        "metric": "CFR+ iterations/s", "value": K / (max_ms * 1e-3), "unit": "iterations/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": it_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (deterministic game tree, no dataset)",
+        "config": dict(cfg, boards_per_rank=s_n_boards(nb_used, rank, world), engine="board-resident (pokerrl_b200/board_engine.py)",
+                       l2="per-rank tables %.1f GB >> 126 MB L2 (no explicit flush)" % (
+                           2 * s_n_boards(nb_used, rank, world) * 14 * rows_bytes / 2 ** 30),
+                       parallelism="boards round-robin over %d ranks; per bottom-up sweep ONE all-reduce of the chance node's "
+                                   "int64 fixed-point sums (%d in the timed region)" % (world, n_allreduce)),
+        "clocks": clocks,
+        "e2e": {"value": K / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 2 * 8 * (K // a.eval_every) / K,
+                "note": "CFRPlus.iteration() facade incl. ChiefBase logging; CFR has no per-step host input - the one-off setup "
+                        "(board enumeration, hand ranks + index tables built on the GPU) is reported under setup"},
+        "setup": {"board_spec_s": t_spec, "engine_build_s": t_setup, "note": "outside every timed number"},
+        "gpu_launches": int(launches), "wall_ms_per_step": wall * 1e3 / K,
+        "exploitability_trace_mbb_per_g": trace[-3:], "roofline": roofline, "matched_instance": matched,
+    }
+    if invariance is not None:
+        out["shard_invariance"] = invariance
+    if world == 1 and not a.no_cpu_baseline:
+        n_it = 6
+        sec, threads, expl = run_cpu_fhp(FHP_CPU_BOARDS, n_it, ncpu)
+        out["matched_instance"].update(cpu_iterations_per_s=1.0 / sec, cpu_threads=threads, same_config=True,
+                                       ratio=out["matched_instance"]["gpu_iterations_per_s"] * sec)
+        out["cpu_baseline"] = {"value": 1.0 / (sec * nb_used / FHP_CPU_BOARDS), "unit": "iterations/s", "cores": threads, "kind": "port",
+                               "sample": "%d CFR+ iterations of oracle/cfr2_oracle.c (float64, OpenMP, %d threads) on the first %d board "
+                                         "classes at %.4f s/iteration, scaled by the board count to the full game (cost is per board); "
+                                         "the reference cannot run Hold'em trees at all (SURVEY.md headline 2)"
+                                         % (n_it, threads, FHP_CPU_BOARDS, sec)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def s_n_boards(n, rank, world):
+    return len(range(rank, n, world))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -294,8 +564,10 @@ def main():
         elif rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": "aux workloads carry their CPU baseline in the main line"}))
         return
+    if a.workload == "fhp":
+        return main_fhp(a, rank, world, local_rank)
     hulh = a.workload == "hulh"
-    fhp = a.workload in ("fhp", "hulh")  # two-card workloads share the sharded engine and the sweep-level roofline
+    fhp = a.workload in ("fhp", "hulh")  # the hulh sub-game runs on the level engine (two chance layers)
     algo_name = "LinearCFR" if hulh else "CFRPlus"
     K = a.steps if a.steps is not None else (40 if fhp else 2000)
     W = max(3, a.warmup if a.warmup is not None else (3 if fhp else 20))
@@ -325,15 +597,7 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the hulh sub-game workload (the float64 oracle is "
                               "exercised on a restricted sub-game in tests/test_gpu_twocard.py)"}))
             return
-        if fhp:
-            K = min(K, 10)
-            full_sec, sec, nb, threads = run_cpu_fhp(32, K, N_CLASSES)
-            v = 1.0 / full_sec
-            sample = ("%d CFR+ iterations of oracle/cfr2_numpy.py (float64 numpy, dense 1326x1326 sign-matrix showdowns) "
-                      "on %d random boards: %.3f s/iteration, extrapolated linearly to the %d board classes of the full "
-                      "game; the reference itself cannot run Hold'em trees" % (K, nb, sec, N_CLASSES))
-            ms = full_sec * 1e3
-        else:
+        if True:
             g, ft = make_tree(a.workload, 20000)
             K = min(K, 200)
             sec, threads = run_cpu_leduc(ft, K, a.eval_every, min(ncpu, 16))
@@ -588,12 +852,6 @@ def main():
         ncpu = os.cpu_count() or 1
         if hulh:
             pass
-        elif fhp:
-            full_sec, sec, nb, threads = run_cpu_fhp(32, 10, N_CLASSES)
-            out["cpu_baseline"] = {"value": 1.0 / full_sec, "unit": "iterations/s", "cores": threads, "kind": "port",
-                                   "sample": "10 CFR+ iterations of oracle/cfr2_numpy.py (float64 numpy) on %d random "
-                                             "boards at %.3f s/iteration, extrapolated linearly to 134 459 board classes; "
-                                             "the reference cannot run Hold'em trees at all (SURVEY.md headline 2)" % (nb, sec)}
         else:
             n = max(2, min(K, int(15.0 / max(0.014 * st["nodes"] / 873586.0, 1e-4))))
             n = (n // a.eval_every) * a.eval_every or n

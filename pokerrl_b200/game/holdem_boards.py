@@ -110,6 +110,19 @@ class BoardSpec:
         1 / C(n_deck - 4, k) unless a subset is given, in which case boards are uniform over the enumerated set."""
         k = rules.N_FLOP_CARDS
         n_deck = rules.N_CARDS_IN_DECK
+        if deck_subset is None and isomorphic and n_deck == 52 and k == 5 and rules.N_SUITS == 4:
+            # the 134 459 classes of the 2 598 960 five-card boards, precomputed by the code below (data/ file written by
+            # tools/gen_iso_classes.py; 8 s of host enumeration otherwise) - counts re-checked on load
+            import os
+            f = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "flop5_iso_classes.npz")
+            if os.path.exists(f):
+                z = np.load(f)
+                reps, orbit = z["boards"], z["orbit"].astype(np.int64)
+                if reps.shape == (134459, 5) and int(orbit.sum()) == comb(52, 5):
+                    perms = suit_permutation_hand_tables(rules.N_RANKS, rules.N_SUITS)
+                    prob = 1.0 / comb(n_deck - 2 * rules.N_HOLE_CARDS, k)
+                    return BoardSpec(reps, np.full(reps.shape[0], prob), orbit / float(perms.shape[0]), perms,
+                                     "%d suit-isomorphism classes of %d boards" % (reps.shape[0], comb(52, 5)))
         if deck_subset is None:
             boards = _combos_52_5() if (n_deck == 52 and k == 5) else all_boards(range(n_deck), k)
             prob = 1.0 / comb(n_deck - 2 * rules.N_HOLE_CARDS, k)
