@@ -169,6 +169,18 @@ def run_cpu_fhp(n_boards, n_iters, threads):
     ranks[1:] = oracle_ranks(bc[1:])
     c = cfr2_c.Oracle2CSolver(ft, ranks, "CFRPlus", n_threads=threads, lean=True)
     c.iteration(1)
+    # thread count: the fastest of {8, 16, 32, 64, all usable} on one iteration each (level-synchronous OpenMP loops stop
+    # scaling - and can slow down badly - once the threads outnumber the cores the container really has)
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else threads
+    best = None
+    for nt in sorted({min(x, usable) for x in (8, 16, 32, 64, usable)}):
+        c.n_threads = c.L.orc2_set_threads(nt)
+        t0 = time.perf_counter()
+        c.iteration(1)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    c.n_threads = c.L.orc2_set_threads(best[1])
     t0 = time.perf_counter()
     c.iteration(n_iters)
     sec = (time.perf_counter() - t0) / n_iters
