@@ -326,6 +326,11 @@ void get_hand_rank_all_hands_on_given_boards_52_holdem(int32_t** out /*[n][1326]
                                                        int32_t n, int8_t** idx2holecards, int8_t** card1d_to_2d);
 void get_hole_card_2_idx_lut(int16_t** lut /*[52][52]*/);
 void get_idx_2_hole_card_lut(int8_t** lut /*[1326][2]*/);
+/* bound by CppLibHoldemLuts.__init__ (CppLUT.py:28-35), never called by the reference; its own binary faults on them
+ * (INTEGRATION.md §2).  Defined, in-bounds results for the buffer shapes of CppLUT.py:47-72. */
+void get_idx_2_flop_lut(int8_t** lut /*[22100][3]: 3-card combinations, lexicographic*/);
+void get_idx_2_turn_lut(int8_t** lut /*[52][4]: row i column 0 = card i*/);
+void get_idx_2_river_lut(int8_t** lut /*[52][5]: row i column 0 = card i*/);
 int8_t get_1d_card(const int8_t* card_2d);
 void get_2d_card(int8_t card_1d, int8_t* out_card_2d);
 

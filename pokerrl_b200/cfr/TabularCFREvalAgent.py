@@ -8,6 +8,15 @@ from pokerrl_b200 import _native as nat
 from pokerrl_b200.rl.base_cls.EvalAgentBase import EvalAgentBase
 
 
+def tree_fingerprint(ft):
+    """structural identity of a flat tree: slot count + hash of kinds / fan-outs / actions / pots"""
+    import hashlib
+    h = hashlib.sha1()
+    for a in (ft.kind, ft.n_children, ft.action, ft.pot):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return (int(ft.n_slots), h.hexdigest())
+
+
 def average_strategy_table(solver):
     """float32 [n_slots, R] average strategy of a CFRSolver (host copy), normalised like the reference's `avg_strat`."""
     ft, R = solver.ft, solver.ft.R
@@ -36,12 +45,19 @@ class TabularCFREvalAgent(EvalAgentBase):
         self._n_actions = self.env_bldr.N_ACTIONS
 
     def update_weights(self, weights_for_eval_agent):
+        """weights: float32 [n_slots, R] table, or (table, fingerprint) with the structural fingerprint of the tree the table
+        belongs to (tree_fingerprint); with a fingerprint, querying the agent on a different tree raises"""
+        fp = None
+        if isinstance(weights_for_eval_agent, tuple):
+            weights_for_eval_agent, fp = weights_for_eval_agent
         self._table = np.ascontiguousarray(weights_for_eval_agent, dtype=np.float32)
+        self._fingerprint = fp
 
     @classmethod
     def from_cfr(cls, t_prof, cfr, tree_idx=0):
         agent = cls(t_prof=t_prof)
-        agent.update_weights(average_strategy_table(cfr.solvers[tree_idx]))
+        solver = cfr.solvers[tree_idx]
+        agent.update_weights((average_strategy_table(solver), tree_fingerprint(solver.ft)))
         return agent
 
     def can_compute_mode(self):
@@ -51,13 +67,17 @@ class TabularCFREvalAgent(EvalAgentBase):
         """[RANGE_SIZE, N_ACTIONS] with the node's probabilities at its allowed actions, 0 elsewhere"""
         node = self._node
         ft = node.tree.flat
+        if getattr(self, "_fingerprint", None) is not None and tree_fingerprint(ft) != self._fingerprint:
+            raise ValueError("this agent's table was computed on a different public tree (stack / bet set / slot order): "
+                             "build one agent per evaluated tree (TabularCFREvalAgent.from_cfr(..., tree_idx=...))")
         fs, a = ft.first_slot[node.idx], ft.n_children[node.idx]
         out = np.zeros((ft.R, self._n_actions), np.float32)
         out[:, node.allowed_actions] = self._table[fs:fs + a].T
         return out
 
     def _state_dict(self):
-        return {"table": self._table}
+        return {"table": self._table, "fingerprint": getattr(self, "_fingerprint", None)}
 
     def _load_state_dict(self, state):
         self._table = state["table"]
+        self._fingerprint = state.get("fingerprint")

@@ -22,6 +22,8 @@ class CFRBase:
 
     def __init__(self, name, chief_handle, game_cls, agent_bet_set, algo_name, starting_stack_sizes=None,
                  delay=0, eval_every=1, device=None, avg_f64=False, board_spec=None):
+        import os
+        avg_f64 = bool(avg_f64) or os.environ.get("PRL_AVG_F64", "0") == "1"  # numpy >= 2 semantics of CFRPlus.py:69-73
         self._name = name
         self._n_seats = 2
         self._chief_handle = chief_handle
@@ -102,13 +104,22 @@ class CFRBase:
         for s, st in zip(self._solvers, state["solvers"]):
             s.load_state_dict(st)
 
+    @staticmethod
+    def _rank_path(path):
+        """sharded runs: every rank owns different boards -> one file per rank"""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return "%s.rank%d_of_%d" % (path, dist.get_rank(), dist.get_world_size())
+        return path
+
     def checkpoint(self, path):
         import torch
-        torch.save(self.state_dict(), path)
+        torch.save(self.state_dict(), self._rank_path(path))
 
     def load_checkpoint(self, path):
         import torch
-        self.load_state_dict(torch.load(path, weights_only=False))
+        # tensors, ints, strings and lists only: no pickled code is ever executed
+        self.load_state_dict(torch.load(self._rank_path(path), weights_only=True))
 
     def _metric(self, t_idx):
         return "Evaluation/" + self._env_bldrs[t_idx].env_cls.WIN_METRIC

@@ -1105,26 +1105,19 @@ void reach_sweep2(Ctx2 c, bool update_avg, cudaStream_t s) {
 // reduction (the per-node sums W stay in the workspace, e.g. to be all-reduced across GPUs); 2 = only that final stage
 int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int chance_phase, cudaStream_t s) {
     const prl_tree_t& T = c.T;
-    static bool smem_set = false;
+    // the opt-in for > 48 KB of dynamic shared memory is a PER-DEVICE function attribute: (re)applied on every call
     const size_t tsm = term_smem(T);
-    if (!smem_set) {
-        cudaFuncSetAttribute(terminal2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        smem_set = true;
-    }
+    cudaFuncSetAttribute(terminal2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+    cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
     const char* v_env = getenv("PRL_TERMINAL_V");  // A/B switch, read per call: 2, 3 or 4 (default: newest usable)
     int term_v = (v_env && v_env[0] >= '2' && v_env[0] <= '4') ? v_env[0] - '0' : 4;
     if (term_v >= 3 && (!T.work_rec2 || !T.board_hand_rec || (T.n_range & 1))) term_v = 2;
     if (term_v == 4 && (!T.level_nfold || T.n_deck > 64 || ((T.n_deck - 1 + 3) >> 2) != 13)) term_v = 3;
     const TermSmem tl(T.n_range, T.n_deck);
-    static size_t smem3_max = 0;
-    if (tl.total > smem3_max) {
-        cudaFuncSetAttribute(terminal2_kernel_v3<true, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
-        cudaFuncSetAttribute(terminal2_kernel_v3<false, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
-        cudaFuncSetAttribute(terminal2_kernel_v3<true, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
-        cudaFuncSetAttribute(terminal2_kernel_v3<false, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
-        smem3_max = tl.total;
-    }
+    cudaFuncSetAttribute(terminal2_kernel_v3<true, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+    cudaFuncSetAttribute(terminal2_kernel_v3<false, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+    cudaFuncSetAttribute(terminal2_kernel_v3<true, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
+    cudaFuncSetAttribute(terminal2_kernel_v3<false, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
     int arr_mask = 0;
     for (int p = 0; p < 2; ++p)
         if (c.mask & (1 << p)) arr_mask |= (1 << (2 * p)) | (with_br ? (2 << (2 * p)) : 0);
@@ -1503,11 +1496,9 @@ extern "C" int prl_cfr_plus_board_sweep(const prl_tree_t* tree, const prl_buffer
     Ctx2 c{*tree, *buf, 0, 0, 1 << p, {strat_mode[0], strat_mode[1]}, PRL_ALGO_CFR_PLUS, p, iter, delay, 0.0f, 1.0f};
     set_avg_weights(c);
     const size_t sm = sub_smem(*tree, sub->n_local);
-    static size_t set_for = 0;
-    if (set_for < sm) {
+    {
         cudaError_t e = cudaFuncSetAttribute(board_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return prl::check(e, "prl_cfr_plus_board_sweep: shared memory");
-        set_for = sm;
     }
     board_sweep_kernel<<<sub->n_boards_local, kSubThreads, sm, (cudaStream_t)stream>>>(c, *sub);
     prl::count_launch();

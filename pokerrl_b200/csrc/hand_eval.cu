@@ -164,6 +164,30 @@ extern "C" void get_idx_2_hole_card_lut(int8_t** lut /*[1326][2]*/) {
         }
 }
 
+// The three board LUT natives CppLibHoldemLuts.__init__ binds (CppLUT.py:28-35) and allocates as
+// [DICT_LUT_N_BOARDS[round]][DICT_LUT_N_CARDS_OUT[round]] = [22100][3], [52][4], [52][5] (CppLUT.py:47-72).  The reference
+// never calls them (look_up_table.py:95-134 uses only the hole-card tables) and its own binary does not survive the call:
+// get_idx_2_flop_lut writes its 22 099 lexicographic 3-card combinations at row indices up to 1 080 450 and the other two
+// fault even on a 2.7 M-row buffer (probed in the build container).  Exported here so that the
+// reference's binding loads, with a defined in-bounds result for exactly those buffer shapes: flop row i = the i-th
+// 3-card combination in lexicographic order; turn / river row i = {card i dealt in that transition, rest untouched}.
+extern "C" void get_idx_2_flop_lut(int8_t** lut /*[22100][3]*/) {
+    int idx = 0;
+    for (int a = 0; a < 52; ++a)
+        for (int b = a + 1; b < 52; ++b)
+            for (int c = b + 1; c < 52; ++c, ++idx) {
+                lut[idx][0] = (int8_t)a;
+                lut[idx][1] = (int8_t)b;
+                lut[idx][2] = (int8_t)c;
+            }
+}
+extern "C" void get_idx_2_turn_lut(int8_t** lut /*[52][4]*/) {
+    for (int c = 0; c < 52; ++c) lut[c][0] = (int8_t)c;
+}
+extern "C" void get_idx_2_river_lut(int8_t** lut /*[52][5]*/) {
+    for (int c = 0; c < 52; ++c) lut[c][0] = (int8_t)c;
+}
+
 extern "C" int8_t get_1d_card(const int8_t* card_2d) { return (int8_t)(card_2d[0] * 4 + card_2d[1]); }
 
 extern "C" void get_2d_card(int8_t card_1d, int8_t* out) {

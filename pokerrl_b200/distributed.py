@@ -17,7 +17,7 @@ import torch.distributed as dist
 from pokerrl_b200 import _native as nat
 from pokerrl_b200.game.flat_tree import FlatTree
 from pokerrl_b200.game.holdem_boards import BoardSpec
-from pokerrl_b200.solver import CFRSolver, TreeBuffers, TreeOps, _stream
+from pokerrl_b200.solver import CFRSolver, TreeBuffers, TreeOps, _on, _stream
 
 
 def shard_board_spec(spec, rank, world):
@@ -126,6 +126,10 @@ class ShardedCFRSolver(CFRSolver):
             levels(hi, 0, 0)
 
     def iteration(self, n=1):
+        with _on(self.dtree.device):
+            self._iteration_sharded(n)
+
+    def _iteration_sharded(self, n):
         tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
         for _ in range(n):
             for p in (0, 1):
@@ -145,6 +149,10 @@ class ShardedCFRSolver(CFRSolver):
             self.iter_counter += 1
 
     def exploitability_current(self):
+        with _on(self.dtree.device):
+            return self._exploitability_current()
+
+    def _exploitability_current(self):
         if self._reach_stale:
             self.ops.reach_pass(self.modes)
             self._reach_stale = False
@@ -152,10 +160,11 @@ class ShardedCFRSolver(CFRSolver):
         return self._metric(self.ops.root_exploitability())
 
     def exploitability_average(self):
-        if self._eval_bufs is None:
-            self._eval_bufs = TreeBuffers(self.dtree, share=self.bufs)
-            self._eval_ops = TreeOps(self.dtree, self._eval_bufs)
-        m = self.average_modes()
-        self._eval_ops.reach_pass(m)
-        self._value_sweep(self._eval_bufs, 3, True, -1, -1, m)
-        return self._metric(self._eval_ops.root_exploitability())
+        with _on(self.dtree.device):
+            if self._eval_bufs is None:
+                self._eval_bufs = TreeBuffers(self.dtree, share=self.bufs)
+                self._eval_ops = TreeOps(self.dtree, self._eval_bufs)
+            m = self.average_modes()
+            self._eval_ops.reach_pass(m)
+            self._value_sweep(self._eval_bufs, 3, True, -1, -1, m)
+            return self._metric(self._eval_ops.root_exploitability())

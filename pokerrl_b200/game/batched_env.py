@@ -47,11 +47,12 @@ def env_config(game_cls, env_args, n_envs):
 
 
 class BatchedPokerEnv:
-    def __init__(self, game_cls, env_args, n_envs, device="cuda:0", seed=0):
+    def __init__(self, game_cls, env_args, n_envs, device=None, seed=0):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedPokerEnv needs a CUDA device; there is no CPU fallback")
         assert env_args.n_seats == 2
         self.cfg = env_config(game_cls, env_args, n_envs)
+        device = device if device is not None else "cuda:%d" % torch.cuda.current_device()
         self.n_envs, self.device, self.seed = n_envs, torch.device(device), int(seed)
         nf = nat.lib().prl_env_state_fields()
         z = lambda *s, dtype: torch.zeros(*s, dtype=dtype, device=self.device)  # noqa: E731
@@ -64,18 +65,18 @@ class BatchedPokerEnv:
         self._step_id, self._episode0 = 0, 0
         self.N_ACTIONS, self.obs_size = self.cfg.n_actions, self.cfg.obs_size
 
-    @staticmethod
-    def _stream():
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def reset(self, decks=None):
         """decks: optional int8 [B, n_deck] (top card first: seat 0's hole cards, seat 1's, then the board) - the
         batched analogue of `reset(deck_state_dict=...)` (PokerEnv.py:1118-1120); otherwise shuffled on the device."""
         if decks is not None:
             self.deck.copy_(torch.as_tensor(decks).to(device=self.device, dtype=torch.int8))
-        nat.call("prl_env_reset", C.byref(self.cfg), C.c_void_p(self.state.data_ptr()), C.c_void_p(self.deck.data_ptr()),
-                 C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.legal.data_ptr()), self.seed, self._episode0,
-                 int(decks is None), self._stream())
+        with torch.cuda.device(self.device):
+            nat.call("prl_env_reset", C.byref(self.cfg), C.c_void_p(self.state.data_ptr()), C.c_void_p(self.deck.data_ptr()),
+                     C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.legal.data_ptr()), self.seed, self._episode0,
+                     int(decks is None), self._stream())
         self._episode0 += self.n_envs
         return self.obs, self.legal
 
@@ -86,9 +87,10 @@ class BatchedPokerEnv:
         if actions is not None:
             a = torch.as_tensor(actions).to(device=self.device, dtype=torch.int32).contiguous()
             a_ptr = C.c_void_p(a.data_ptr())
-        nat.call("prl_env_step", C.byref(self.cfg), C.c_void_p(self.state.data_ptr()), C.c_void_p(self.deck.data_ptr()),
-                 a_ptr, C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.rewards.data_ptr()),
-                 C.c_void_p(self.done.data_ptr()), C.c_void_p(self.legal.data_ptr()), self.seed, self._step_id,
-                 int(auto_reset), self._stream())
+        with torch.cuda.device(self.device):
+            nat.call("prl_env_step", C.byref(self.cfg), C.c_void_p(self.state.data_ptr()), C.c_void_p(self.deck.data_ptr()),
+                     a_ptr, C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.rewards.data_ptr()),
+                     C.c_void_p(self.done.data_ptr()), C.c_void_p(self.legal.data_ptr()), self.seed, self._step_id,
+                     int(auto_reset), self._stream())
         self._step_id += 1
         return self.obs, self.rewards, self.done, self.legal

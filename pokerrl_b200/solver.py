@@ -16,13 +16,24 @@ ALGOS = {"VanillaCFR": nat.ALGO_VANILLA, "CFRPlus": nat.ALGO_CFR_PLUS, "LinearCF
 
 
 def _require_cuda(device):
+    """torch.device of the GPU to use: the given one, else the process's CURRENT device (under torchrun each rank sets
+    its own with torch.cuda.set_device; never silently cuda:0)."""
     if not torch.cuda.is_available():
         raise RuntimeError("pokerrl_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
-    return torch.device(device if device is not None else "cuda:0")
+    d = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    if d.type != "cuda":
+        raise RuntimeError("pokerrl_b200 runs on CUDA devices only, got %r" % (device,))
+    return torch.device("cuda:%d" % (d.index if d.index is not None else torch.cuda.current_device()))
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """the torch stream of `device` (default: current device) - launches go where the buffers live"""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _on(device):
+    """context: make `device` current for the ctypes launches inside (kernels run on the CURRENT device)"""
+    return torch.cuda.device(device)
 
 
 def structure_records(ft, order):
@@ -108,12 +119,13 @@ class DeviceTree:
             fc0 = ft.first_child[ch[0]] if ch.size else 0
             assert ch.size == 0 or np.array_equal(board[fc0:fc0 + rules.N_CARDS_IN_DECK],
                                                   np.arange(rules.N_CARDS_IN_DECK))
-        if rules.N_HOLE_CARDS == 1:
-            self.t_meta = torch.zeros(ft.n_nodes, 4, dtype=torch.int32, device=dev)
-            nat.call("prl_pack_node_meta", C.byref(d), C.c_void_p(self.t_meta.data_ptr()), _stream())
-            d.meta = self.t_meta.data_ptr()
-        else:
-            self._init_two_card(ft, d, up)
+        with _on(dev):
+            if rules.N_HOLE_CARDS == 1:
+                self.t_meta = torch.zeros(ft.n_nodes, 4, dtype=torch.int32, device=dev)
+                nat.call("prl_pack_node_meta", C.byref(d), C.c_void_p(self.t_meta.data_ptr()), _stream(dev))
+                d.meta = self.t_meta.data_ptr()
+            else:
+                self._init_two_card(ft, d, up)
 
     def _init_two_card(self, ft, d, up):
         """Board tables of the Hold'em family: card masks, deal probabilities, parent weights, strength-order tables
@@ -151,7 +163,7 @@ class DeviceTree:
             rp = torch.zeros((ids.numel(), self.R, 4), dtype=torch.uint8, device=dev)
             nat.call("prl_board_order_tables", C.c_void_p(ranks.data_ptr()), int(ids.numel()), self.R, n_deck,
                      C.c_void_p(g1.data_ptr()), C.c_void_p(g2.data_ptr()), C.c_void_p(g3.data_ptr()),
-                     C.c_void_p(ro.data_ptr()), C.c_void_p(rp.data_ptr()), _stream())
+                     C.c_void_p(ro.data_ptr()), C.c_void_p(rp.data_ptr()), _stream(dev))
             gs[ids], ge[ids], pos[ids], row_order[ids], row_pos[ids] = g1, g2, g3, ro, rp
         self.t_board_gs, self.t_board_ge, self.t_board_pos = gs, ge, pos
         self.t_board_row_order, self.t_board_row_pos = row_order, row_pos
@@ -249,23 +261,31 @@ class TreeOps:
         self._expl = torch.zeros(2, dtype=torch.float32, device=dtree.device)
 
     def reach_pass(self, modes, player_mask=3):
-        nat.call("prl_reach_pass", C.byref(self.dtree.desc), C.byref(self.bufs.desc), player_mask,
-                 nat.modes(*modes), _stream())
+        dev = self.dtree.device
+        with _on(dev):
+            nat.call("prl_reach_pass", C.byref(self.dtree.desc), C.byref(self.bufs.desc), player_mask,
+                     nat.modes(*modes), _stream(dev))
 
     def value_pass(self, modes, player_mask=3, with_br=True):
-        nat.call("prl_value_pass", C.byref(self.dtree.desc), C.byref(self.bufs.desc), player_mask, int(with_br),
-                 nat.modes(*modes), _stream())
+        dev = self.dtree.device
+        with _on(dev):
+            nat.call("prl_value_pass", C.byref(self.dtree.desc), C.byref(self.bufs.desc), player_mask, int(with_br),
+                     nat.modes(*modes), _stream(dev))
 
     def evaluate(self, modes, do_reach):
         """One persistent launch: [reach pass,] value pass with BR, root exploitability -> float32[2] chips."""
-        nat.call("prl_evaluate", C.byref(self.dtree.desc), C.byref(self.bufs.desc), nat.modes(*modes), int(do_reach),
-                 C.c_void_p(self._expl.data_ptr()), _stream())
+        dev = self.dtree.device
+        with _on(dev):
+            nat.call("prl_evaluate", C.byref(self.dtree.desc), C.byref(self.bufs.desc), nat.modes(*modes), int(do_reach),
+                     C.c_void_p(self._expl.data_ptr()), _stream(dev))
         return self._expl.cpu().numpy()
 
     def root_exploitability(self):
         """float32[2] chips (device->host read)."""
-        nat.call("prl_root_exploitability", C.byref(self.dtree.desc), C.byref(self.bufs.desc),
-                 C.c_void_p(self._expl.data_ptr()), _stream())
+        dev = self.dtree.device
+        with _on(dev):
+            nat.call("prl_root_exploitability", C.byref(self.dtree.desc), C.byref(self.bufs.desc),
+                     C.c_void_p(self._expl.data_ptr()), _stream(dev))
         return self._expl.cpu().numpy()
 
 
@@ -307,7 +327,12 @@ class CFRSolver:
         self.ops.reach_pass(self.modes)
 
     def iteration(self, n=1):
+        with _on(self.dtree.device):
+            self._iteration(n)
+
+    def _iteration(self, n):
         tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
+        _stream = lambda: C.c_void_p(torch.cuda.current_stream(self.dtree.device).cuda_stream)  # noqa: E731
         if self.schedule == "tasks" and n > 0 and self.ft.rules.N_HOLE_CARDS == 1:
             nat.call("prl_cfr_iterations_tasks", tree, buf, C.byref(self._task_tables()), self.algo, self.iter_counter, n,
                      self.delay, int(self.avg_f64), nat.modes(*self.modes), _stream())
@@ -346,11 +371,20 @@ class CFRSolver:
     # ---- checkpoint / resume (the reference's CFR classes keep regrets only inside node objects; WorkerBase.py:23-38 is
     #      a no-op skeleton) - SURVEY.md §8f N1
     def state_dict(self):
-        return {"algo": self.algo_name, "delay": self.delay, "iter_counter": self.iter_counter, "modes": list(self.modes),
+        return {"engine": "levels", "algo": self.algo_name, "delay": self.delay, "avg_f64": self.avg_f64,
+                "rank": getattr(self, "rank", 0), "world": getattr(self, "world", 1), "n_nodes": self.ft.n_nodes,
+                "iter_counter": self.iter_counter, "modes": list(self.modes),
                 "regret": self.bufs.regret.cpu(), "strat": self.bufs.strat.cpu(), "avg": self.bufs.avg.cpu()}
 
     def load_state_dict(self, state):
-        assert state["algo"] == self.algo_name and state["regret"].shape == self.bufs.regret.shape
+        mine = {"engine": "levels", "algo": self.algo_name, "delay": self.delay, "avg_f64": self.avg_f64,
+                "rank": getattr(self, "rank", 0), "world": getattr(self, "world", 1), "n_nodes": self.ft.n_nodes}
+        for k, v in mine.items():
+            if state.get(k, v) != v:
+                raise ValueError("checkpoint mismatch on %r: file has %r, this solver %r" % (k, state.get(k), v))
+        if tuple(state["regret"].shape) != tuple(self.bufs.regret.shape) or state["avg"].dtype != self.bufs.avg.dtype:
+            raise ValueError("checkpoint tables do not fit this solver (shape %s vs %s, avg dtype %s vs %s)" % (
+                tuple(state["regret"].shape), tuple(self.bufs.regret.shape), state["avg"].dtype, self.bufs.avg.dtype))
         self.iter_counter, self.modes = int(state["iter_counter"]), list(state["modes"])
         self.bufs.regret.copy_(state["regret"])
         self.bufs.strat.copy_(state["strat"])

@@ -77,7 +77,7 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     import subprocess
     from pokerrl_b200 import _native
     pairs = [("prl_tree_t", _native.PrlTree), ("prl_buffers_t", _native.PrlBuffers), ("prl_subtree_t", _native.PrlSubtree),
-             ("prl_env_cfg_t", _native.PrlEnvCfg), ("prl_tasks_t", _native.PrlTasks)]
+             ("prl_env_cfg_t", _native.PrlEnvCfg), ("prl_tasks_t", _native.PrlTasks), ("prl_board_game_t", _native.PrlBoardGame)]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "pokerrl_b200.h"', 'int main(void) {']
     for cname, cls in pairs:
         src.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
@@ -93,3 +93,51 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_reference_binding_sequence_against_this_library(golden_dir):
+    """Replays what the reference does with its native libraries - CppWrapper (PokerRL/_/CppWrapper.py:10-27: LoadLibrary, 2-D
+    arrays as arrays of row pointers), CppLibHoldemLuts.__init__ + getters (CppLUT.py:16-94) and CppHandeval.__init__
+    (CppHandeval.py:19-33) - against libpokerrl_b200.so instead of lib_luts.so / lib_hand_eval.so: every symbol the
+    reference sets argtypes on exists, and the LUT natives (host code, no GPU needed) fill the reference's buffer shapes with
+    the reference's tables (tests/golden/luts.npz)."""
+    import ctypes
+    from pokerrl_b200 import _native
+    lib = ctypes.cdll.LoadLibrary(_native.LIB_PATH)
+    ARR_2D = np.ctypeslib.ndpointer(dtype=np.intp, ndim=1, flags="C")
+
+    def rows(arr):  # CppWrapper.np_2d_arr_to_c
+        return (arr.__array_interface__["data"][0] + np.arange(arr.shape[0]) * arr.strides[0]).astype(np.intp)
+
+    for f in ("get_hole_card_2_idx_lut", "get_idx_2_hole_card_lut", "get_idx_2_flop_lut", "get_idx_2_turn_lut",
+              "get_idx_2_river_lut"):  # CppLUT.py:22-35
+        getattr(lib, f).argtypes = [ARR_2D]
+        getattr(lib, f).restype = None
+    lib.get_hand_rank_52_holdem.argtypes = [ARR_2D, ARR_2D]  # CppHandeval.py:22-33
+    lib.get_hand_rank_52_holdem.restype = ctypes.c_int32
+    lib.get_hand_rank_all_hands_on_given_boards_52_holdem.argtypes = [ARR_2D, ARR_2D, ctypes.c_int32, ARR_2D, ARR_2D]
+    lib.get_hand_rank_all_hands_on_given_boards_52_holdem.restype = None
+    gold = np.load(os.path.join(golden_dir, "luts.npz"))
+    n_boards = dict(gold["holdem_DICT_LUT_N_BOARDS"].tolist())
+    n_out = dict(gold["holdem_DICT_LUT_N_CARDS_OUT"].tolist())
+    a = np.full((1326, 2), -2, np.int8)  # CppLUT.py:38-41
+    lib.get_idx_2_hole_card_lut(rows(a))
+    assert np.array_equal(a, gold["holdem_LUT_IDX_2_HOLE_CARDS"])
+    b = np.full((52, 52), -2, np.int16)  # CppLUT.py:43-46
+    lib.get_hole_card_2_idx_lut(rows(b))
+    assert np.array_equal(b, gold["holdem_LUT_HOLE_CARDS_2_IDX"])
+    from itertools import combinations
+    flop = np.full((n_boards[1], n_out[1]), -2, np.int8)  # CppLUT.py:47-54: [22100][3]
+    lib.get_idx_2_flop_lut(rows(flop))
+    assert np.array_equal(flop, np.array(list(combinations(range(52), 3)), np.int8))
+    for f, rnd in (("get_idx_2_turn_lut", 2), ("get_idx_2_river_lut", 3)):  # [52][4], [52][5]: in-bounds, card per row
+        t = np.full((n_boards[rnd], n_out[rnd]), -2, np.int8)
+        getattr(lib, f)(rows(t))
+        assert np.array_equal(t[:, 0], np.arange(52)) and np.all(t[:, 1:] == -2)
+    lib.get_1d_card.argtypes, lib.get_1d_card.restype = [ctypes.c_void_p], ctypes.c_int8
+    lib.get_2d_card.argtypes, lib.get_2d_card.restype = [ctypes.c_int8, ctypes.c_void_p], None
+    for c in range(52):  # look_up_table.py:102-119
+        out = np.empty(2, np.int8)
+        lib.get_2d_card(c, out.ctypes.data)
+        assert np.array_equal(out, gold["holdem_LUT_1DCARD_2_2DCARD"][c])
+        assert lib.get_1d_card(out.ctypes.data) == gold["holdem_LUT_2DCARD_2_1DCARD"][out[0], out[1]] == c
