@@ -167,25 +167,6 @@ int prl_cfr_half_iteration(const prl_tree_t* tree, const prl_buffers_t* buf, int
 int prl_cfr_iterations(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int iter0, int n_iters, int delay,
                        int avg_f64, const int* strat_mode, prl_stream_t stream);
 
-/* Subtree ("task") schedule of the one-card sweeps (pokerrl_b200/task_schedule.py): the tree is cut by subtree size into a
- * small trunk and many closed subtrees; one thread block runs all levels of a subtree with block barriers, so an iteration
- * needs 4 grid-wide ordering points (kernel boundaries) instead of one per tree level and sweep.  Same per-node arithmetic
- * as prl_cfr_iterations (the same device functions), only the order of independent nodes differs. */
-typedef struct {
-    int32_t n_tasks;
-    int32_t n_levels;            /* tree levels (entries of trunk_start - 1) */
-    const int32_t* order;        /* DEVICE int32[n_nodes]: task-major work list, the trunk's nodes last */
-    const int32_t* task_ptr;     /* DEVICE int32[n_tasks + 1]: segments (task, local level) of task t, top level first */
-    const int32_t* seg_start;    /* DEVICE int32[n_seg + 1]: entries of segment s = order[seg_start[s] : seg_start[s+1]] */
-    const int32_t* seg_nonterm;  /* DEVICE int32[n_seg]: non-terminal entries of the segment (they come first) */
-    const int64_t* trunk_start;  /* HOST int64[n_levels + 1]: trunk entries of tree level d in `order` */
-} prl_tasks_t;
-
-/* prl_cfr_iterations with the task schedule.  Reach rows must be current on entry (as for prl_cfr_iterations) and are
- * current on return.  One-card trees only. */
-int prl_cfr_iterations_tasks(const prl_tree_t* tree, const prl_buffers_t* buf, const prl_tasks_t* tasks, int algo, int iter0,
-                             int n_iters, int delay, int avg_f64, const int* strat_mode, prl_stream_t stream);
-
 /* Exploitability evaluation in one persistent launch (_CFRBase._log_curr_strat_expl :198-216 / _evaluate_avg_strats
  * :218-262; eval/br/LocalBRMaster.py:67-80): optional reach pass for both seats (do_reach), value pass with best
  * response for both seats, root exploitability -> out_expl = DEVICE float[2] (chips). */

@@ -29,7 +29,6 @@ def lib():
         L.orc_value_pass.argtypes = [tp, bp, C.c_int, C.c_int, ip]
         L.orc_root_exploitability.argtypes = [tp, bp, C.c_void_p]
         L.orc_cfr_half_iteration.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip]
-        L.orc_cfr_iterations_tasks.argtypes = [tp, bp, C.POINTER(nat.PrlTasks), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip]
         _lib = L
     return _lib
 
@@ -85,25 +84,7 @@ class OracleCSolver:
         self.modes = [nat.STRAT_UNIFORM64, nat.STRAT_UNIFORM64]
         self.L.orc_reach_pass(C.byref(self.tree), C.byref(self.bufs), 3, nat.modes(*self.modes))
 
-    def set_task_schedule(self, threshold):
-        """run iteration() in the subtree ("task") order of pokerrl_b200/task_schedule.py (host pointers)"""
-        from pokerrl_b200.task_schedule import TaskSchedule
-        ts = TaskSchedule(self.ft, threshold)
-        self._task_arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (ts.order, ts.task_ptr, ts.seg_start, ts.seg_nonterm)]
-        self._task_trunk = np.ascontiguousarray(ts.trunk_start, dtype=np.int64)
-        k = nat.PrlTasks()
-        k.n_tasks, k.n_levels = ts.n_tasks, self.ft.n_levels
-        k.order, k.task_ptr, k.seg_start, k.seg_nonterm = (a.ctypes.data for a in self._task_arrs)
-        k.trunk_start = self._task_trunk.ctypes.data
-        self._tasks = k
-
     def iteration(self, n=1):
-        if getattr(self, "_tasks", None) is not None and n > 0:
-            self.L.orc_cfr_iterations_tasks(C.byref(self.tree), C.byref(self.bufs), C.byref(self._tasks), self.algo,
-                                            self.iter_counter, n, self.delay, int(self.avg_f64), nat.modes(*self.modes))
-            self.modes = [nat.STRAT_F32, nat.STRAT_F32]
-            self.iter_counter += n
-            return
         for _ in range(n):
             for p in (0, 1):
                 self.L.orc_cfr_half_iteration(C.byref(self.tree), C.byref(self.bufs), self.algo, p,

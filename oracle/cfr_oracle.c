@@ -291,66 +291,3 @@ int orc_cfr_half_iteration(const prl_tree_t* tree, const prl_buffers_t* buf, int
     reach_levels(&c, 1);
     return 0;
 }
-
-/* ------------------------------------------------------------------------------------------ task schedule
- * Host restatement of the ORCHESTRATION of prl_cfr_iterations_tasks (pokerrl_b200/csrc/cfr_levels.cu:
- * run_task_iterations): same launch sequence - [pending top-down sweep of the previous seat + bottom-up sweep of seat p]
- * over the tasks, then the trunk bottom-up and top-down, one closing top-down sweep of the tasks - with the per-node
- * functions of this file.  `tasks` carries HOST pointers here.  tests/test_task_schedule.py checks that this order gives
- * bit-for-bit the results of the level order, i.e. that the pending-sweep bookkeeping (seat, iteration number, strategy
- * sources) is right; the GPU side mirrors it statement by statement. */
-static void reach_from_parents(const ctx_t* c, const int32_t* list, int lo, int hi) {
-    const prl_tree_t* T = c->T;
-    for (int t = lo; t < hi; ++t) {
-        const int n = list[t];
-        if (n == 0) reach_node(c, 0, 1); /* the root's own row */
-        const int fc = T->first_child[n];
-        if (fc < 0) continue;
-        for (int k = 0; k < T->n_children[n]; ++k) reach_node(c, fc + k, 1);
-    }
-}
-
-static void value_list(const ctx_t* c, const int32_t* list, int lo, int hi) {
-    for (int t = lo; t < hi; ++t) value_node(c, list[t], 0, 1);
-}
-
-static ctx_t reach_ctx(const prl_tree_t* T, const prl_buffers_t* B, const int* mode, int algo, int q, int it, int delay,
-                       int avg_f64) {
-    ctx_t c = {T, B, 1 << q, {mode[0], mode[1]}, algo, q, it, delay, avg_f64};
-    c.mode[q] = PRL_STRAT_F32;
-    return c;
-}
-
-static void task_sweep(const ctx_t* cr, const ctx_t* cv, const prl_tasks_t* K, int do_reach, int do_value) {
-    for (int t = 0; t < K->n_tasks; ++t) {
-        const int s0 = K->task_ptr[t], s1 = K->task_ptr[t + 1];
-        if (do_reach)
-            for (int s = s0; s < s1; ++s) reach_from_parents(cr, K->order, K->seg_start[s], K->seg_start[s] + K->seg_nonterm[s]);
-        if (do_value)
-            for (int s = s1 - 1; s >= s0; --s) value_list(cv, K->order, K->seg_start[s], K->seg_start[s + 1]);
-    }
-}
-
-int orc_cfr_iterations_tasks(const prl_tree_t* T, const prl_buffers_t* B, const prl_tasks_t* K, int algo, int iter0,
-                             int n_iters, int delay, int avg_f64, const int* strat_mode) {
-    int mode[2] = {strat_mode[0], strat_mode[1]};
-    int pend_q = -1, pend_iter = 0;
-    for (int it = 0; it < n_iters; ++it) {
-        for (int p = 0; p < 2; ++p) {
-            const ctx_t cv = {T, B, 1 << p, {mode[0], mode[1]}, algo, p, iter0 + it, delay, avg_f64};
-            const ctx_t cr_pending = reach_ctx(T, B, mode, algo, pend_q < 0 ? 0 : pend_q, pend_iter, delay, avg_f64);
-            task_sweep(&cr_pending, &cv, K, pend_q >= 0, 1);
-            mode[p] = PRL_STRAT_F32;
-            const ctx_t cr = reach_ctx(T, B, mode, algo, p, iter0 + it, delay, avg_f64);
-            for (int d = K->n_levels - 1; d >= 0; --d) value_list(&cv, K->order, (int)K->trunk_start[d], (int)K->trunk_start[d + 1]);
-            for (int d = 0; d < K->n_levels; ++d) reach_from_parents(&cr, K->order, (int)K->trunk_start[d], (int)K->trunk_start[d + 1]);
-            pend_q = p;
-            pend_iter = iter0 + it;
-        }
-    }
-    if (pend_q >= 0) {
-        const ctx_t cr = reach_ctx(T, B, mode, algo, pend_q, pend_iter, delay, avg_f64);
-        task_sweep(&cr, &cr, K, 1, 0);
-    }
-    return 0;
-}

@@ -34,11 +34,6 @@ class PrlTree(C.Structure):
     ]
 
 
-class PrlTasks(C.Structure):
-    _fields_ = [("n_tasks", C.c_int32), ("n_levels", C.c_int32), ("order", C.c_void_p), ("task_ptr", C.c_void_p),
-                ("seg_start", C.c_void_p), ("seg_nonterm", C.c_void_p), ("trunk_start", C.c_void_p)]
-
-
 class PrlBuffers(C.Structure):
     _fields_ = [("reach", C.c_void_p), ("ev", C.c_void_p), ("ev_br", C.c_void_p), ("regret", C.c_void_p),
                 ("strat", C.c_void_p), ("avg", C.c_void_p), ("workspace", C.c_void_p),
@@ -103,9 +98,6 @@ def lib():
     L.prl_launch_count.restype = C.c_ulonglong
     L.prl_cfr_iterations.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_void_p]
     L.prl_evaluate.argtypes = [tp, bp, ip, C.c_int, C.c_void_p, C.c_void_p]
-    L.prl_cfr_iterations_tasks.argtypes = [tp, bp, C.POINTER(PrlTasks), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip,
-                                           C.c_void_p]
-    L.prl_cfr_iterations_tasks.restype = C.c_int
     L.prl_pack_node_meta.argtypes = [tp, C.c_void_p, C.c_void_p]
     for f in ("prl_reach_pass", "prl_value_pass", "prl_root_exploitability", "prl_cfr_half_iteration", "prl_cfr_sweep", "prl_pack_node_meta", "prl_cfr_iterations",
               "prl_evaluate"):

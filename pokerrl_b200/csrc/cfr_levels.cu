@@ -475,8 +475,8 @@ __device__ __forceinline__ void root_exploitability(const prl_tree_t& T, const p
     out[p] = s;
 }
 
-// THREADS: block size = threads per SM (one block per SM).  512 is the measured default (128 registers per thread);
-// 1024 caps the kernel at 64 registers for twice the warps per SM (PRL_PERSISTENT_THREADS=1024, unmeasured so far).
+// THREADS: block size = threads per SM (one block per SM): 512 at 128 registers per thread.  A 1024-thread / 64-register
+// instantiation measured 1 668 vs 1 677 iterations/s on the B_5 tree (profiles/r02_h_leduc_schedules.md) and was removed.
 template <int R, int NS, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) cfr_iterations_kernel(Ctx c, const Levels lv, const int n_iters) {
     cg::grid_group grid = cg::this_grid();
@@ -698,13 +698,6 @@ template <int R>
 int launch_iterations(Ctx& c, Levels& lv, int n_iters, cudaStream_t s) {
     int grid = 0;
     void* args[] = {&c, &lv, &n_iters};
-    const char* wide = getenv("PRL_PERSISTENT_THREADS");  // experiment switch: 1024 threads per SM at 64 registers
-    if (wide && atoi(wide) == 1024) {
-        if (int e = coop_grid(cfr_iterations_kernel<R, 2, 1024>, &grid, 1024)) return e;
-        prl::count_launch();
-        return prl::check(cudaLaunchCooperativeKernel((void*)cfr_iterations_kernel<R, 2, 1024>, dim3(grid), dim3(1024), args, 0, s),
-                          "prl_cfr_iterations");
-    }
     if (int e = coop_grid(cfr_iterations_kernel<R, 2, kPThreads>, &grid)) return e;
     prl::count_launch();
     return prl::check(cudaLaunchCooperativeKernel((void*)cfr_iterations_kernel<R, 2, kPThreads>, dim3(grid), dim3(kPThreads), args, 0, s),
@@ -719,103 +712,6 @@ int launch_evaluate(Ctx& c, Levels& lv, int do_reach, float* out, cudaStream_t s
     prl::count_launch();
     return prl::check(cudaLaunchCooperativeKernel((void*)evaluate_kernel<R, 2>, dim3(grid), dim3(kPThreads), args, 0, s),
                       "prl_evaluate");
-}
-
-// ---- subtree ("task") schedule: see prl_tasks_t in include/pokerrl_b200.h and pokerrl_b200/task_schedule.py -------------
-// One block per task.  A task is a complete subtree, so every row it reads was written either by an earlier kernel
-// (the task root's reach row, by the trunk) or by this block earlier in this launch - __syncthreads() orders those.
-constexpr int kTaskThreads = 128;
-constexpr int kTrunkThreads = 1024;
-
-struct TaskTable {
-    const int* task_ptr;
-    const int* seg_start;
-    const int* seg_nonterm;
-};
-
-// cr: context of the pending top-down sweep (seat q: mask = 1 << q, upd_p = q, its iteration number, mode[q] = F32);
-// cv: context of the bottom-up sweep of the seat being updated.  Both contexts carry the task-major work list as T.order.
-template <int R, int NS>
-__global__ void __launch_bounds__(kTaskThreads, 8) task_sweep_kernel(const Ctx cr, const Ctx cv, const TaskTable tt,
-                                                                  const int do_reach, const int do_value) {
-    constexpr int NPW = LaneMap<R>::NPW;
-    const int s0 = tt.task_ptr[blockIdx.x], s1 = tt.task_ptr[blockIdx.x + 1];
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (do_reach) {
-        for (int s = s0; s < s1; ++s) {
-            const int lo = tt.seg_start[s], hi = lo + tt.seg_nonterm[s], ng = groups_of(hi - lo, NPW);
-            for (int grp = warp; grp < ng; grp += nwarps) reach_group<R, true>(cr, lo, hi, grp);
-            __syncthreads();
-        }
-    }
-    if (do_value) {
-        for (int s = s1 - 1; s >= s0; --s) {
-            const int lo = tt.seg_start[s], hi = tt.seg_start[s + 1], ng = groups_of(hi - lo, NPW);
-            for (int grp = warp; grp < ng; grp += nwarps) value_group<R, NS, false, true>(cv, lo, hi, grp);
-            __syncthreads();
-        }
-    }
-}
-
-// the trunk in ONE block: bottom-up sweep of seat p (cv), then its top-down sweep with the average update (cr)
-template <int R, int NS>
-__global__ void __launch_bounds__(kTrunkThreads, 1) trunk_sweep_kernel(const Ctx cr, const Ctx cv, const Levels lv) {
-    constexpr int NPW = LaneMap<R>::NPW;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int d = lv.n_levels - 1; d >= 0; --d) {
-        const int lo = lv.start[d], hi = lv.start[d + 1], ng = groups_of(hi - lo, NPW);
-        for (int grp = warp; grp < ng; grp += nwarps) value_group<R, NS, false, true>(cv, lo, hi, grp);
-        __syncthreads();
-    }
-    for (int d = 0; d < lv.n_levels; ++d) {
-        const int lo = lv.start[d], hi = lv.start[d + 1], ng = groups_of(hi - lo, NPW);
-        for (int grp = warp; grp < ng; grp += nwarps) reach_group<R, true>(cr, lo, hi, grp);
-        __syncthreads();
-    }
-}
-
-template <int R>
-int run_task_iterations(const prl_tree_t& T0, const prl_buffers_t& B, const prl_tasks_t& K, int algo, int iter0, int n_iters,
-                        int delay, int avg_f64, const int* strat_mode, cudaStream_t s) {
-    prl_tree_t T = T0;
-    T.order = K.order;  // the group functions index the work list through T.order
-    Levels lv;
-    lv.timeline = nullptr;
-    lv.n_levels = K.n_levels;
-    for (int d = 0; d <= K.n_levels; ++d) lv.start[d] = (int)K.trunk_start[d];
-    const bool has_trunk = lv.start[K.n_levels] > lv.start[0];
-    const TaskTable tt{K.task_ptr, K.seg_start, K.seg_nonterm};
-    int mode[2] = {strat_mode[0], strat_mode[1]};
-    int pend_q = -1, pend_iter = 0;  // top-down sweep of the tasks that is still owed (seat, its iteration number)
-    auto reach_ctx = [&](int q, int it) {
-        Ctx c{T, B, 0, 0, 1 << q, {mode[0], mode[1]}, algo, q, it, delay, avg_f64};
-        c.mode[q] = PRL_STRAT_F32;  // the seat's strategy lives in the float table after its update
-        return c;
-    };
-    for (int it = 0; it < n_iters; ++it) {
-        for (int p = 0; p < 2; ++p) {  // _CFRBase.py:123-128
-            const Ctx cv{T, B, 0, 0, 1 << p, {mode[0], mode[1]}, algo, p, iter0 + it, delay, avg_f64};
-            const Ctx cr_pending = reach_ctx(pend_q < 0 ? 0 : pend_q, pend_iter);
-            if (K.n_tasks > 0) {
-                task_sweep_kernel<R, 2><<<K.n_tasks, kTaskThreads, 0, s>>>(cr_pending, cv, tt, pend_q >= 0, 1);
-                prl::count_launch();
-            }
-            mode[p] = PRL_STRAT_F32;
-            const Ctx cr = reach_ctx(p, iter0 + it);
-            if (has_trunk) {
-                trunk_sweep_kernel<R, 2><<<1, kTrunkThreads, 0, s>>>(cr, cv, lv);
-                prl::count_launch();
-            }
-            pend_q = p;
-            pend_iter = iter0 + it;
-        }
-    }
-    if (pend_q >= 0 && K.n_tasks > 0) {
-        const Ctx cr = reach_ctx(pend_q, pend_iter);
-        task_sweep_kernel<R, 2><<<K.n_tasks, kTaskThreads, 0, s>>>(cr, cr, tt, 1, 0);
-        prl::count_launch();
-    }
-    return prl::check(cudaGetLastError(), "prl_cfr_iterations_tasks");
 }
 
 }  // namespace
@@ -843,21 +739,6 @@ extern "C" int prl_cfr_iterations(const prl_tree_t* tree, const prl_buffers_t* b
     if (int e = make_levels(tree, &lv)) return e;
     return tree->n_range == 6 ? launch_iterations<6>(c, lv, n_iters, (cudaStream_t)stream)
                               : launch_iterations<24>(c, lv, n_iters, (cudaStream_t)stream);
-}
-
-extern "C" int prl_cfr_iterations_tasks(const prl_tree_t* tree, const prl_buffers_t* buf, const prl_tasks_t* tasks, int algo,
-                                        int iter0, int n_iters, int delay, int avg_f64, const int* strat_mode,
-                                        prl_stream_t stream) {
-    if (int e = check_tree(tree)) return e;
-    if (!tasks || !tasks->order || !tasks->task_ptr || !tasks->seg_start || !tasks->seg_nonterm || !tasks->trunk_start)
-        return prl::fail("prl_cfr_iterations_tasks: incomplete task tables");
-    if (tasks->n_levels != tree->n_levels || tasks->n_levels > kMaxLevels) return prl::fail("prl_cfr_iterations_tasks: bad n_levels");
-    if (algo < 0 || algo > 2 || n_iters < 0) return prl::fail("prl_cfr_iterations_tasks: bad algo / n_iters");
-    if (algo != PRL_ALGO_CFR_PLUS && avg_f64) return prl::fail("avg_f64 only applies to CFR+");
-    if (n_iters == 0) return 0;
-    return tree->n_range == 6
-               ? run_task_iterations<6>(*tree, *buf, *tasks, algo, iter0, n_iters, delay, avg_f64, strat_mode, (cudaStream_t)stream)
-               : run_task_iterations<24>(*tree, *buf, *tasks, algo, iter0, n_iters, delay, avg_f64, strat_mode, (cudaStream_t)stream);
 }
 
 extern "C" int prl_evaluate(const prl_tree_t* tree, const prl_buffers_t* buf, const int* strat_mode, int do_reach,

@@ -297,16 +297,8 @@ class CFRSolver:
     strategy is a separate, optional evaluation (the reference does both every iteration).
     """
 
-    def __init__(self, ft, algo="CFRPlus", delay=0, device=None, avg_f64=False, persistent=True, schedule=None,
-                 task_threshold=None):
+    def __init__(self, ft, algo="CFRPlus", delay=0, device=None, avg_f64=False, persistent=True):
         self.persistent = bool(persistent)  # one cooperative launch per call instead of one launch per tree level
-        # "tasks": subtree schedule of the one-card sweeps (pokerrl_b200/task_schedule.py; experimental, see DESIGN.md §9)
-        schedule = schedule if schedule is not None else os.environ.get("PRL_SCHEDULE", "levels")
-        task_threshold = task_threshold if task_threshold is not None else int(os.environ.get("PRL_TASK_THRESHOLD", "1024"))
-        if schedule not in ("levels", "tasks"):
-            raise ValueError("schedule must be 'levels' or 'tasks'")
-        self.schedule, self.task_threshold = schedule, int(task_threshold)
-        self._tasks = None
         self.ft = ft
         self.algo_name = algo
         self.algo = ALGOS[algo]
@@ -333,12 +325,6 @@ class CFRSolver:
     def _iteration(self, n):
         tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
         _stream = lambda: C.c_void_p(torch.cuda.current_stream(self.dtree.device).cuda_stream)  # noqa: E731
-        if self.schedule == "tasks" and n > 0 and self.ft.rules.N_HOLE_CARDS == 1:
-            nat.call("prl_cfr_iterations_tasks", tree, buf, C.byref(self._task_tables()), self.algo, self.iter_counter, n,
-                     self.delay, int(self.avg_f64), nat.modes(*self.modes), _stream())
-            self.modes = [nat.STRAT_F32, nat.STRAT_F32]
-            self.iter_counter += n
-            return
         if self.persistent and n > 0:
             nat.call("prl_cfr_iterations", tree, buf, self.algo, self.iter_counter, n, self.delay,
                      int(self.avg_f64), nat.modes(*self.modes), _stream())
@@ -351,22 +337,6 @@ class CFRSolver:
                          int(self.avg_f64), nat.modes(*self.modes), _stream())
                 self.modes[p] = nat.STRAT_F32
             self.iter_counter += 1
-
-    def _task_tables(self):
-        if self._tasks is None:
-            from pokerrl_b200.task_schedule import TaskSchedule
-            ts = TaskSchedule(self.ft, self.task_threshold)
-            dev = self.dtree.device
-            self._task_sched = ts
-            self._task_arrays = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
-                                 for a in (ts.order, ts.task_ptr, ts.seg_start, ts.seg_nonterm)]
-            self._task_trunk_start = np.ascontiguousarray(ts.trunk_start, dtype=np.int64)
-            d = nat.PrlTasks()
-            d.n_tasks, d.n_levels = ts.n_tasks, self.ft.n_levels
-            d.order, d.task_ptr, d.seg_start, d.seg_nonterm = (a.data_ptr() for a in self._task_arrays)
-            d.trunk_start = self._task_trunk_start.ctypes.data
-            self._tasks = d
-        return self._tasks
 
     # ---- checkpoint / resume (the reference's CFR classes keep regrets only inside node objects; WorkerBase.py:23-38 is
     #      a no-op skeleton) - SURVEY.md §8f N1
