@@ -195,27 +195,6 @@ int prl_value_levels(const prl_tree_t* tree, const prl_buffers_t* buf, int playe
 int prl_reach_update(const prl_tree_t* tree, const prl_buffers_t* buf, int algo, int p, int iter, int delay,
                      prl_stream_t stream);
 
-/* Post-deal subtree of ONE board of a game with a single chance layer (identical for every board): local nodes in
- * breadth-first order, local 0 = the node right after the deal; global node id of local node i on the j-th board of this
- * rank = node_base[i] + j * node_m[i] + node_k[i] (the flat-tree numbering of game/flat_tree.py). */
-typedef struct {
-    int32_t n_local;          /* <= 16 */
-    int32_t chance_node;      /* global id of the chance node whose children are the boards */
-    int32_t n_boards_local;   /* boards (children of that chance node) in this tree */
-    int32_t first_board;      /* global board id of the first of them (ids are consecutive) */
-    int32_t node_base[16], node_m[16], node_k[16];
-    int8_t kind[16], parent[16], first_child[16], n_children[16], acted_last[16];
-    float pot[16];
-} prl_subtree_t;
-
-/* Fused CFR+ half-iteration of seat p over all board subtrees (one CTA per board, node vectors in shared memory): replaces,
- * for the post-deal levels, the bottom-up value/regret sweep AND the top-down reach/average sweep of
- * prl_cfr_half_iteration (_CFRBase.py:123-128 + CFRPlus.py:37-87).  Reads reach[1-p] of the chance node and the
- * strategy table, updates regret / strat / avg rows of p's post-deal nodes, writes ev[p] of each board's root node.
- * Finish the half-iteration with prl_value_levels(chance level .. 0) and prl_reach_levels(0 .. chance level). */
-int prl_cfr_plus_board_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, const prl_subtree_t* sub, int p, int iter,
-                             int delay, const int* strat_mode, prl_stream_t stream);
-
 /* Top-down reach sweep over tree levels level_lo..level_hi only (StrategyFiller.py:118-146); algo >= 0 adds the
  * average-strategy update of seat upd_p (as in prl_cfr_half_iteration). */
 int prl_reach_levels(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int algo, int upd_p, int iter,

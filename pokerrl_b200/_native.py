@@ -40,14 +40,6 @@ class PrlBuffers(C.Structure):
                 ("workspace_bytes", C.c_uint64)]
 
 
-class PrlSubtree(C.Structure):
-    _fields_ = [("n_local", C.c_int32), ("chance_node", C.c_int32), ("n_boards_local", C.c_int32),
-                ("first_board", C.c_int32), ("node_base", C.c_int32 * 16), ("node_m", C.c_int32 * 16),
-                ("node_k", C.c_int32 * 16), ("kind", C.c_int8 * 16), ("parent", C.c_int8 * 16),
-                ("first_child", C.c_int8 * 16), ("n_children", C.c_int8 * 16), ("acted_last", C.c_int8 * 16),
-                ("pot", C.c_float * 16)]
-
-
 class PrlBoardGame(C.Structure):
     _fields_ = [("n_boards", C.c_int32), ("n_range", C.c_int32), ("ld", C.c_int32), ("n_deck", C.c_int32),
                 ("n_local", C.c_int32), ("frac_bits", C.c_int32), ("grid", C.c_int32), ("eq_const", C.c_float),
@@ -106,9 +98,8 @@ def lib():
                                    C.c_int, C.c_void_p]
     L.prl_reach_update.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.prl_value_levels.restype = L.prl_reach_update.restype = C.c_int
-    L.prl_cfr_plus_board_sweep.argtypes = [tp, bp, C.POINTER(PrlSubtree), C.c_int, C.c_int, C.c_int, ip, C.c_void_p]
     L.prl_reach_levels.argtypes = [tp, bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_void_p]
-    L.prl_cfr_plus_board_sweep.restype = L.prl_reach_levels.restype = C.c_int
+    L.prl_reach_levels.restype = C.c_int
     L.prl_board_order_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
     L.prl_board_order_tables.restype = C.c_int

@@ -15,7 +15,6 @@
 // would only add work - see DESIGN.md §6.
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "pokerrl_b200.h"
 #include "prl_common.cuh"
@@ -1109,13 +1108,11 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
     const size_t tsm = term_smem(T);
     cudaFuncSetAttribute(terminal2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
     cudaFuncSetAttribute(terminal2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-    const char* v_env = getenv("PRL_TERMINAL_V");  // A/B switch, read per call: 2, 3 or 4 (default: newest usable)
-    int term_v = (v_env && v_env[0] >= '2' && v_env[0] <= '4') ? v_env[0] - '0' : 4;
-    if (term_v >= 3 && (!T.work_rec2 || !T.board_hand_rec || (T.n_range & 1))) term_v = 2;
-    if (term_v == 4 && (!T.level_nfold || T.n_deck > 64 || ((T.n_deck - 1 + 3) >> 2) != 13)) term_v = 3;
+    // terminal rows: fold rows and showdown rows in their own kernels (packed records, cp.async staging, 52-card decks); the
+    // record-free kernel is the fallback for callers that pass NULL records or another deck size
+    const bool packed = T.work_rec2 && T.board_hand_rec && !(T.n_range & 1) && T.level_nfold && T.n_deck <= 64 &&
+                        ((T.n_deck - 1 + 3) >> 2) == 13;
     const TermSmem tl(T.n_range, T.n_deck);
-    cudaFuncSetAttribute(terminal2_kernel_v3<true, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
-    cudaFuncSetAttribute(terminal2_kernel_v3<false, kSegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
     cudaFuncSetAttribute(terminal2_kernel_v3<true, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
     cudaFuncSetAttribute(terminal2_kernel_v3<false, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total);
     int arr_mask = 0;
@@ -1128,7 +1125,7 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
         if (n_term > 0 && chance_phase != 2) {
             c.lo = lo + n_nonterm;
             c.n = n_term;
-            if (term_v == 4) {  // fold rows (first among the terminals of a level) and showdown rows launched apart
+            if (packed) {  // fold rows (first among the terminals of a level) and showdown rows launched apart
                 const int n_fold = (int)T.level_nfold[d];
                 if (n_fold > 0) {
                     c.n = n_fold;
@@ -1143,10 +1140,6 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
                     else terminal2_kernel_v3<false, 13><<<c.n, kTermThreads, tl.total, s>>>(c);
                     prl::count_launch();
                 }
-            } else if (term_v == 3) {
-                if (with_br) terminal2_kernel_v3<true, kSegMax><<<n_term, kTermThreads, tl.total, s>>>(c);
-                else terminal2_kernel_v3<false, kSegMax><<<n_term, kTermThreads, tl.total, s>>>(c);
-                prl::count_launch();
             } else {
                 if (with_br) terminal2_kernel<true><<<n_term, kTermThreads, tsm, s>>>(c);
                 else terminal2_kernel<false><<<n_term, kTermThreads, tsm, s>>>(c);
@@ -1271,238 +1264,6 @@ extern "C" int prl_board_order_tables(const int32_t* ranks, int n_boards, int n_
     prl::count_launch();
     prl::count_launch();
     return prl::check(cudaGetLastError(), "prl_board_order_tables");
-}
-
-// =====================================================================================================================
-// Fused board-subtree sweep (CFR+ hot path of games with ONE chance layer, e.g. Flop5Holdem): one CTA per board keeps the
-// whole post-deal subtree (<= 16 nodes x R floats = 85 KB) in shared memory and does, for seat p,
-//   A. opponent reach top-down (strategy rows of the opponent streamed from the tables),
-//   B. terminal rows in place (same fold / showdown arithmetic as terminal2_kernel),
-//   C. values bottom-up with regret update, regret matching and the CFR+ average update of p's rows,
-//   D. the subtree-root value row -> ev[p] of the board's root node (the trunk's chance reduction consumes it).
-// Node vectors of board nodes never touch HBM: traffic = table rows + 18.5 KB of board tables per board.
-// Steps A and C are independent per hand (no barriers); only the terminal rows cooperate across hands.
-// =====================================================================================================================
-namespace {
-
-constexpr int kSubThreads = 512;
-constexpr int kMaxLocal = 16;
-
-__device__ __forceinline__ int sub_node(const prl_subtree_t& S, int i, int j) { return S.node_base[i] + j * S.node_m[i] + S.node_k[i]; }
-
-__global__ void __launch_bounds__(kSubThreads) board_sweep_kernel(const Ctx2 c, const prl_subtree_t S) {
-    extern __shared__ float smem[];
-    const int R = c.T.n_range, ld = c.T.ld, n_deck = c.T.n_deck, row_len = n_deck - 1;
-    const int xs = (R + 3) & ~3;                 // row stride of the node vectors in shared memory
-    float* X = smem;                              // [n_local][xs]  opponent reach on the way down, ev[p] on the way up
-    float* srt = X + (size_t)S.n_local * xs;      // [R + 1]
-    float* rp = srt + R + 1;                      // [n_deck][kRowStride]
-    float* red = rp + n_deck * kRowStride;        // [32]
-    float* wsum = red + 32;                       // [kSubThreads / 32 + 1]
-    const int j = blockIdx.x;                     // local board index
-    const int b = S.first_board + j;              // global board id
-    const int p = c.upd_p, opp = 1 - p;
-    const size_t N = (size_t)c.T.n_nodes;
-    const unsigned long long bmask = c.T.board_mask[b];
-    const float prob = c.T.board_prob[b];
-    const float K = c.T.eq_const;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-
-    // ---- A. opponent reach, top-down, per hand.  All table loads of a hand are issued before the first use.
-    const float* trunk_ro = c.B.reach + ((size_t)opp * N + S.chance_node) * ld;
-    for (int h = threadIdx.x; h < R; h += blockDim.x) {
-        float so[kMaxLocal];
-#pragma unroll
-        for (int i = 1; i < kMaxLocal; ++i)
-            so[i] = (i < S.n_local && S.kind[S.parent[i]] == opp) ? c.B.strat[(size_t)c.T.slot[sub_node(S, i, j)] * ld + h] : 1.0f;
-        X[h] = hand_blocked(c.T, h, bmask) ? 0.0f : trunk_ro[h] * prob;
-#pragma unroll
-        for (int i = 1; i < kMaxLocal; ++i)
-            if (i < S.n_local) X[(size_t)i * xs + h] = X[(size_t)S.parent[i] * xs + h] * so[i];
-    }
-    __syncthreads();
-
-    // ---- B. terminal rows, in place
-    const int16_t* gs_tab = c.T.board_gs + (size_t)b * R;
-    const int16_t* ge_tab = c.T.board_ge + (size_t)b * R;
-    const int16_t* pos_tab = c.T.board_pos + (size_t)b * R;
-    const int16_t* row_order = c.T.board_row_order + (size_t)b * n_deck * row_len;
-    const uchar4* row_pos = reinterpret_cast<const uchar4*>(c.T.board_row_pos) + (size_t)b * R;
-    for (int i = 0; i < S.n_local; ++i) {
-        const int kind = S.kind[i];
-        if (kind < PRL_KIND_FOLD) continue;
-        float* ro = X + (size_t)i * xs;
-        float part = 0.0f;
-        for (int h = threadIdx.x; h < R; h += blockDim.x) part += ro[h];
-        const float T = block_sum(part, red);
-        for (int cc = warp; cc < n_deck; cc += n_warps) {  // card-row prefix sums: one warp per card row
-            const int16_t* ord = row_order + cc * row_len;
-            const int h0 = (lane < row_len) ? ord[lane] : -1;
-            const int h1 = (lane + 32 < row_len) ? ord[lane + 32] : -1;
-            float v0 = (h0 >= 0) ? ro[h0] : 0.0f, v1 = (h1 >= 0) ? ro[h1] : 0.0f;
-            for (int o = 1; o < 32; o <<= 1) {
-                const float t0 = __shfl_up_sync(0xffffffffu, v0, o), t1 = __shfl_up_sync(0xffffffffu, v1, o);
-                if (lane >= o) { v0 += t0; v1 += t1; }
-            }
-            v1 += __shfl_sync(0xffffffffu, v0, 31);
-            float* row = rp + cc * kRowStride;
-            if (lane == 0) row[0] = 0.0f;
-            if (lane < row_len) row[lane + 1] = v0;
-            if (lane + 32 < row_len) row[lane + 33] = v1;
-        }
-        const float scale = K * S.pot[i] * 0.5f;
-        if (kind == PRL_KIND_FOLD) {
-            __syncthreads();
-            const float sgn = (S.acted_last[i] == p) ? -1.0f : 1.0f;
-            for (int h = threadIdx.x; h < R; h += blockDim.x) {
-                const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
-                float e = (T - rp[c1 * kRowStride + row_len] - rp[c2 * kRowStride + row_len] + ro[h]) * sgn;
-                if (((bmask >> c1) | (bmask >> c2)) & 1ull) e = 0.0f;
-                ro[h] = e * scale;
-            }
-        } else {
-            for (int q = threadIdx.x; q <= R; q += blockDim.x) srt[q] = 0.0f;
-            __syncthreads();
-            for (int h = threadIdx.x; h < R; h += blockDim.x) {
-                const int ps = pos_tab[h];
-                if (ps >= 0) srt[ps] = ro[h];
-            }
-            __syncthreads();
-            const int per = (R + 1 + blockDim.x - 1) / blockDim.x;
-            const int i0 = threadIdx.x * per, i1 = min(R + 1, i0 + per);
-            float loc = 0.0f;
-            for (int q = i0; q < i1; ++q) loc += srt[q];
-            float inc = loc;
-            for (int o = 1; o < 32; o <<= 1) {
-                const float t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) wsum[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                float w = (lane < n_warps) ? wsum[lane] : 0.0f;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float t = __shfl_up_sync(0xffffffffu, w, o);
-                    if (lane >= o) w += t;
-                }
-                if (lane < n_warps) wsum[lane] = w;
-            }
-            __syncthreads();
-            float run = inc - loc + (warp > 0 ? wsum[warp - 1] : 0.0f);
-            for (int q = i0; q < i1; ++q) {
-                const float x = srt[q];
-                srt[q] = run;
-                run += x;
-            }
-            __syncthreads();
-            for (int h = threadIdx.x; h < R; h += blockDim.x) {
-                const int gs = gs_tab[h];
-                float v = 0.0f;
-                if (gs >= 0) {
-                    const int ge = ge_tab[h];
-                    const int c1 = c.T.hand_cards[2 * h], c2 = c.T.hand_cards[2 * h + 1];
-                    const uchar4 q = row_pos[h];
-                    const float* r1 = rp + c1 * kRowStride;
-                    const float* r2 = rp + c2 * kRowStride;
-                    const float all = srt[gs] - (srt[R] - srt[ge]);
-                    const float rows = (r1[q.x] - (r1[row_len] - r1[q.z])) + (r2[q.y] - (r2[row_len] - r2[q.w]));
-                    v = (all - rows) * scale;
-                }
-                ro[h] = v;
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- C. values bottom-up with the update of seat p's rows, per hand; D. root row out.
-    // Every table element this hand needs (strategy, regret, average of p's action rows) is requested up front, the
-    // stores come last: one memory round trip per hand instead of one per row.
-    const float w_lin = (float)(c.iter + 1);
-    float* ev_root = c.B.ev + ((size_t)p * N + sub_node(S, 0, j)) * ld;
-    const int m = c.mode[p];
-    for (int h = threadIdx.x; h < R; h += blockDim.x) {
-        float sg[kMaxLocal], rg[kMaxLocal], ag[kMaxLocal];  // indexed by the local CHILD node of the action
-#pragma unroll
-        for (int i = 1; i < kMaxLocal; ++i) {
-            const bool mine = i < S.n_local && S.kind[S.parent[i]] == p;
-            const size_t off = mine ? (size_t)c.T.slot[sub_node(S, i, j)] * ld + h : 0;
-            sg[i] = mine ? c.B.strat[off] : 0.0f;
-            rg[i] = mine ? c.B.regret[off] : 0.0f;
-            ag[i] = mine ? ((const float*)c.B.avg)[off] : 0.0f;
-        }
-#pragma unroll 1
-        for (int i = S.n_local - 1; i >= 0; --i) {
-            const int kind = S.kind[i];
-            if (kind >= PRL_KIND_FOLD) continue;
-            const int fc = S.first_child[i], A = S.n_children[i];
-            float v = 0.0f;
-            if (kind != p) {
-                for (int k = 0; k < A; ++k) v += X[(size_t)(fc + k) * xs + h];
-            } else {
-                for (int k = 0; k < A; ++k) {
-                    const float sk = (m == PRL_STRAT_UNIFORM64) ? 1.0f / (float)A : sg[fc + k];
-                    v += sk * X[(size_t)(fc + k) * xs + h];
-                }
-                float ssum = 0.0f;
-                for (int k = 0; k < A; ++k) {
-                    const float d = X[(size_t)(fc + k) * xs + h] - v;
-                    float r;
-                    if (c.algo == PRL_ALGO_CFR_PLUS) r = fmaxf(d + rg[fc + k], 0.0f);
-                    else if (c.algo == PRL_ALGO_LINEAR) r = w_lin * d + rg[fc + k];
-                    else r = d + rg[fc + k];
-                    rg[fc + k] = r;
-                    ssum += fmaxf(r, 0.0f);
-                }
-                const float uni = 1.0f / (float)A;
-                const float inv = (ssum > 0.0f) ? 1.0f / ssum : 0.0f;
-                for (int k = 0; k < A; ++k) {
-                    const float sk = (ssum > 0.0f) ? fmaxf(rg[fc + k], 0.0f) * inv : uni;
-                    sg[fc + k] = sk;
-                    if (c.iter >= c.delay) ag[fc + k] = c.m_old * ag[fc + k] + c.m_new * sk;  // CFRPlus.py:65-87
-                }
-            }
-            X[(size_t)i * xs + h] = v;
-        }
-#pragma unroll
-        for (int i = 1; i < kMaxLocal; ++i) {
-            if (i < S.n_local && S.kind[S.parent[i]] == p) {
-                const size_t off = (size_t)c.T.slot[sub_node(S, i, j)] * ld + h;
-                c.B.strat[off] = sg[i];
-                c.B.regret[off] = rg[i];
-                ((float*)c.B.avg)[off] = ag[i];
-            }
-        }
-        ev_root[h] = X[h];
-    }
-}
-
-size_t sub_smem(const prl_tree_t& T, int n_local) {
-    const size_t xs = (T.n_range + 3) & ~3;
-    return sizeof(float) * ((size_t)n_local * xs + T.n_range + 1 + (size_t)T.n_deck * kRowStride + 32 + kSubThreads / 32 + 1);
-}
-
-}  // namespace
-
-// CFR+ half-iteration of seat p on all boards of the (single) chance layer, fused per board: reads reach[1-p] and the
-// strategy tables, updates regret / strat / avg rows of p's post-deal decision nodes and writes ev[p] of every board's
-// root node.  The caller then finishes the bottom-up sweep on the trunk (prl_value_levels from the chance level up) and
-// refreshes reach[p] of the trunk (prl_reach_levels).  Reach rows of post-deal nodes are NOT maintained by this path.
-extern "C" int prl_cfr_plus_board_sweep(const prl_tree_t* tree, const prl_buffers_t* buf, const prl_subtree_t* sub, int p,
-                                        int iter, int delay, const int* strat_mode, prl_stream_t stream) {
-    if (!tree || tree->n_hole != 2) return prl::fail("prl_cfr_plus_board_sweep: two-card trees only");
-    if (int e = check_tree2(tree)) return e;
-    if (!sub || sub->n_local < 1 || sub->n_local > kMaxLocal) return prl::fail("prl_cfr_plus_board_sweep: subtree of 1..16 nodes");
-    if (strat_mode[1 - p] != PRL_STRAT_F32) return prl::fail("prl_cfr_plus_board_sweep: the opponent's strategy must live in the float table");
-    Ctx2 c{*tree, *buf, 0, 0, 1 << p, {strat_mode[0], strat_mode[1]}, PRL_ALGO_CFR_PLUS, p, iter, delay, 0.0f, 1.0f};
-    set_avg_weights(c);
-    const size_t sm = sub_smem(*tree, sub->n_local);
-    {
-        cudaError_t e = cudaFuncSetAttribute(board_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return prl::check(e, "prl_cfr_plus_board_sweep: shared memory");
-    }
-    board_sweep_kernel<<<sub->n_boards_local, kSubThreads, sm, (cudaStream_t)stream>>>(c, *sub);
-    prl::count_launch();
-    return prl::check(cudaGetLastError(), "prl_cfr_plus_board_sweep");
 }
 
 // Top-down reach sweep restricted to tree levels level_lo..level_hi (the rows of level_lo - 1 must be current); with

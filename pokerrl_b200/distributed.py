@@ -51,7 +51,7 @@ class ShardedCFRSolver(CFRSolver):
     world == 1 (or no process group) runs the same split schedule without communication."""
 
     def __init__(self, game_cls, env_args, board_spec, algo="CFRPlus", delay=0, device=None, rank=0, world=1,
-                 group=None, root_actions=None, fused=False):
+                 group=None, root_actions=None):
         self.rank, self.world, self.group = rank, world, group
         ft = FlatTree(game_cls, env_args, board_spec=shard_board_spec(board_spec, rank, world) if world > 1 else board_spec,
                       root_actions=root_actions)
@@ -68,21 +68,7 @@ class ShardedCFRSolver(CFRSolver):
                 self._n_boundary[d] = int((ch & (ft.cdepth[lo:hi] == 0)).sum())
         self._chance_levels = [d for d in self._n_chance if self._n_boundary[d] > 0]
         self.n_allreduce = 0
-        # CFR+ on a tree with ONE chance layer and a small post-deal subtree (Flop5Holdem): optional fused per-board sweeps
-        # (board subtree in shared memory; correct but, in round 1, ~15 % SLOWER than the level sweeps - DESIGN.md §9 -
-        # hence off by default)
-        self._sub = None
-        st = ft.board_subtree() if (fused and algo == "CFRPlus") else None
-        if st is not None:
-            d = nat.PrlSubtree()
-            d.n_local, d.chance_node = st["n_local"], st["chance_node"]
-            d.n_boards_local, d.first_board = st["n_boards_local"], st["first_board"]
-            for i in range(st["n_local"]):
-                d.node_base[i], d.node_m[i], d.node_k[i] = st["node_base"][i], st["node_m"][i], st["node_k"][i]
-                d.kind[i], d.parent[i], d.first_child[i] = st["kind"][i], st["parent"][i], st["first_child"][i]
-                d.n_children[i], d.acted_last[i], d.pot[i] = st["n_children"][i], st["acted_last"][i], st["pot"][i]
-            self._sub, self._chance_level = d, st["chance_level"]
-        self._reach_stale = False  # fused sweeps do not maintain the reach rows of post-deal nodes
+        self._reach_stale = False
 
     def reset(self):
         super().reset()  # includes a full reach pass
@@ -133,19 +119,9 @@ class ShardedCFRSolver(CFRSolver):
         tree, buf = C.byref(self.dtree.desc), C.byref(self.bufs.desc)
         for _ in range(n):
             for p in (0, 1):
-                if self._sub is not None and self.modes[1 - p] == nat.STRAT_F32:
-                    # fused path: board subtrees in shared memory, then the trunk levels with the usual kernels
-                    nat.call("prl_cfr_plus_board_sweep", tree, buf, C.byref(self._sub), p, self.iter_counter,
-                             self.delay, nat.modes(*self.modes), _stream())
-                    self._value_sweep(self.bufs, 1 << p, False, self.algo, p, self.modes, top=self._chance_level)
-                    self.modes[p] = nat.STRAT_F32
-                    nat.call("prl_reach_levels", tree, buf, 1 << p, self.algo, p, self.iter_counter, self.delay,
-                             nat.modes(*self.modes), 0, self._chance_level, _stream())
-                    self._reach_stale = True
-                else:
-                    self._value_sweep(self.bufs, 1 << p, False, self.algo, p, self.modes)
-                    self.modes[p] = nat.STRAT_F32
-                    nat.call("prl_reach_update", tree, buf, self.algo, p, self.iter_counter, self.delay, _stream())
+                self._value_sweep(self.bufs, 1 << p, False, self.algo, p, self.modes)
+                self.modes[p] = nat.STRAT_F32
+                nat.call("prl_reach_update", tree, buf, self.algo, p, self.iter_counter, self.delay, _stream())
             self.iter_counter += 1
 
     def exploitability_current(self):

@@ -94,7 +94,7 @@ def test_sharded_schedule_single_rank_equals_plain_solver():
     ft = fhp_tree(spec)
     g = games.Flop5Holdem
     args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=[1.0])
-    a, b = CFRSolver(ft, "CFRPlus"), ShardedCFRSolver(g, args, spec, "CFRPlus", fused=False)
+    a, b = CFRSolver(ft, "CFRPlus"), ShardedCFRSolver(g, args, spec, "CFRPlus")
     for _ in range(3):
         a.iteration(1)
         b.iteration(1)
@@ -135,40 +135,15 @@ def test_multi_street_subgame_matches_oracle():
         assert abs(a - b) <= 5e-5 * abs(b), (t, a, b)
 
 
-def test_fused_board_sweep_matches_level_sweeps():
-    """The fused per-board CFR+ kernel (node vectors in shared memory) against the level-synchronous kernels."""
-    from pokerrl_b200.distributed import ShardedCFRSolver
-    from pokerrl_b200.game import games
-    spec = random_board_spec(40, 11)
-    g = games.Flop5Holdem
-    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=[1.0])
-    a = ShardedCFRSolver(g, args, spec, "CFRPlus", fused=False)
-    b = ShardedCFRSolver(g, args, spec, "CFRPlus", fused=True)
-    assert b._sub is not None and a._sub is None
-    for t in range(6):
-        a.iteration(1)
-        b.iteration(1)
-        # regrets agree to float32 round-off (strategies are not compared element-wise: regret matching turns a
-        # round-off-sized regret into a pure strategy, SURVEY.md appendix C)
-        x = a.bufs.regret.cpu().numpy().astype(np.float64)
-        y = b.bufs.regret.cpu().numpy().astype(np.float64)
-        _close("regret it%d" % t, y, x, tol=5e-5)
-        ea, eb = a.exploitability_current(), b.exploitability_current()
-        assert abs(ea - eb) <= 5e-5 * abs(ea), (t, ea, eb)
-        ea, eb = a.exploitability_average(), b.exploitability_average()
-        assert abs(ea - eb) <= 5e-5 * abs(ea), (t, ea, eb)
-
-
 @pytest.mark.parametrize("algo", ["CFRPlus", "LinearCFR"])
 def test_kernel_variants_agree(algo, monkeypatch):
     """The record-free fallbacks of the C ABI (NULL node_rec2 / work_rec2 / board_hand_rec: tiled row kernels with
-    pointer chains, table-reading terminal kernel) and the terminal kernel generations (default 4: fold rows apart; 3: one
-    kernel, cp.async staging; 2: direct loads) follow the same trajectory."""
+    pointer chains, table-reading terminal kernel) follow the same trajectory as the default kernels."""
     from pokerrl_b200.solver import CFRSolver
     ft = fhp_tree(random_board_spec(6, 11))
     ref = None
-    for env in ({}, {"PRL_TERMINAL_V": "3"}, {"PRL_TERMINAL_V": "2"}, {"PRL_NO_NODE_REC": "1", "PRL_NO_HAND_REC": "1"}):
-        for k in ("PRL_TERMINAL_V", "PRL_NO_NODE_REC", "PRL_NO_HAND_REC"):
+    for env in ({}, {"PRL_NO_HAND_REC": "1"}, {"PRL_NO_NODE_REC": "1", "PRL_NO_HAND_REC": "1"}):
+        for k in ("PRL_NO_NODE_REC", "PRL_NO_HAND_REC"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
