@@ -200,6 +200,13 @@ int prl_reach_update(const prl_tree_t* tree, const prl_buffers_t* buf, int algo,
 int prl_reach_levels(const prl_tree_t* tree, const prl_buffers_t* buf, int player_mask, int algo, int upd_p, int iter,
                      int delay, const int* strat_mode, int level_lo, int level_hi, prl_stream_t stream);
 
+/* Batched StrategyFiller._fill_with_agent_policy (StrategyFiller.py:88-116): probs = DEVICE float[n_decision][n_range]
+ * [n_actions] (the agent's get_a_probs_for_each_hand for every decision node at once, EvalAgentBase.py:39-44), dec_of_slot /
+ * action_of_slot = DEVICE int32[n_slots] (decision node index and discrete action of every table row) -> out = DEVICE
+ * float[n_slots][ld] strategy table (`strat` of prl_buffers_t). */
+int prl_gather_agent_policy(const float* probs, int n_actions, const int32_t* dec_of_slot, const int32_t* action_of_slot,
+                            int n_slots, int n_range, int ld, float* out, prl_stream_t stream);
+
 /* Strength-order tables of complete boards for the two-card showdown rows: ranks = DEVICE int32[n_boards][n_range]
  * (prl_hand_rank_boards; -1 = blocked) -> gs / ge / pos = DEVICE int16[n_boards][n_range], row_order = DEVICE
  * int16[n_boards][n_deck][n_deck-1], row_pos = DEVICE uint8[n_boards][n_range][4] (see prl_tree_t). */

@@ -107,6 +107,9 @@ def lib():
     L.prl_hand_rank_7.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     for f in ("prl_hand_rank_boards", "prl_hand_rank_7"):
         getattr(L, f).restype = C.c_int
+    L.prl_gather_agent_policy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p]
+    L.prl_gather_agent_policy.restype = C.c_int
     gp = C.POINTER(PrlBoardGame)
     L.prl_board_layout.argtypes = [C.POINTER(C.c_int32)]
     L.prl_board_grid.argtypes = []

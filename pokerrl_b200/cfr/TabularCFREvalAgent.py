@@ -75,6 +75,22 @@ class TabularCFREvalAgent(EvalAgentBase):
         out[:, node.allowed_actions] = self._table[fs:fs + a].T
         return out
 
+    def get_a_probs_for_public_tree(self, tree):
+        """all decision nodes at once: [n_decision, R, N_ACTIONS] on the tree's device (one scatter of the table rows)"""
+        import torch
+        ft = tree.flat
+        if getattr(self, "_fingerprint", None) is not None and tree_fingerprint(ft) != self._fingerprint:
+            raise ValueError("this agent's table was computed on a different public tree")
+        dev = tree.dtree.device
+        dec = tree.decision_nodes()
+        dec_idx = np.full(ft.n_nodes, -1, np.int64)
+        dec_idx[dec] = np.arange(dec.size)
+        child = np.nonzero(ft.slot >= 0)[0]
+        out = torch.zeros((dec.size, ft.R, self._n_actions), dtype=torch.float32, device=dev)
+        tab = torch.from_numpy(self._table).to(dev)  # [n_slots, R]
+        out[torch.from_numpy(dec_idx[ft.parent[child]]).to(dev), :, torch.from_numpy(ft.action[child].astype(np.int64)).to(dev)] = tab
+        return out
+
     def _state_dict(self):
         return {"table": self._table, "fingerprint": getattr(self, "_fingerprint", None)}
 

@@ -1284,3 +1284,25 @@ extern "C" int prl_reach_levels(const prl_tree_t* tree, const prl_buffers_t* buf
     }
     return prl::check(cudaGetLastError(), "prl_reach_levels");
 }
+
+// Batched StrategyFiller._fill_with_agent_policy (StrategyFiller.py:88-116): the agent answered for ALL decision nodes at
+// once - probs[d][h][a] over the env's N_ACTIONS - and table row `slot` (child of decision node dec_of_slot[slot], reached by
+// discrete action action_of_slot[slot]) takes probs[dec][.][action] (the reference's `agent_strat[:, allowed_actions]`, :111).
+namespace {
+__global__ void gather_agent_policy_kernel(const float* __restrict__ probs, int n_actions, const int32_t* __restrict__ dec_of_slot,
+                                           const int32_t* __restrict__ action_of_slot, int n_range, int ld, float* __restrict__ out) {
+    const int slot = blockIdx.x;
+    const float* src = probs + (size_t)dec_of_slot[slot] * n_range * n_actions + action_of_slot[slot];
+    float* dst = out + (size_t)slot * ld;
+    for (int h = threadIdx.x; h < ld; h += blockDim.x) dst[h] = (h < n_range) ? src[(size_t)h * n_actions] : 0.0f;
+}
+}  // namespace
+
+extern "C" int prl_gather_agent_policy(const float* probs, int n_actions, const int32_t* dec_of_slot, const int32_t* action_of_slot,
+                                       int n_slots, int n_range, int ld, float* out, prl_stream_t stream) {
+    if (n_slots <= 0) return 0;
+    if (!probs || !dec_of_slot || !action_of_slot || !out || ld < n_range) return prl::fail("prl_gather_agent_policy: bad arguments");
+    gather_agent_policy_kernel<<<n_slots, 256, 0, (cudaStream_t)stream>>>(probs, n_actions, dec_of_slot, action_of_slot, n_range, ld, out);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_gather_agent_policy");
+}

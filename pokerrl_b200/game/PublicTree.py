@@ -145,7 +145,10 @@ class PublicTree:
     CHANCE_ID = "Ch"
 
     def __init__(self, env_bldr, stack_size, stop_at_street, put_out_new_round_after_limit=False,
-                 is_debugging=False, device=None):
+                 is_debugging=False, device=None, board_spec=None):
+        """board_spec (extension, two-card games): the boards of the chance layer (holdem_boards.BoardSpec); default = all
+        boards of the game as suit-isomorphism classes"""
+        self._board_spec = board_spec
         self._env_bldr = env_bldr
         self._stack_size = stack_size
         self._is_debugging = is_debugging
@@ -184,11 +187,12 @@ class PublicTree:
     # ---- build
     def build_tree(self):
         args = self._env_bldr.args_for_stack(self._stack_size)
-        self.flat = FlatTree(self._env_bldr.env_cls, args, stop_at_street=self._stop_at_street_arg)
+        self.flat = FlatTree(self._env_bldr.env_cls, args, stop_at_street=self._stop_at_street_arg, board_spec=self._board_spec)
         self.dtree = DeviceTree(self.flat, self._device)
         self.bufs = TreeBuffers(self.dtree, avg_dtype=torch.float64)
         self.ops = TreeOps(self.dtree, self.bufs)
         self.modes = [nat.STRAT_UNIFORM64, nat.STRAT_UNIFORM64]
+        self._slot_maps = None
         self._cache = {}
         self._root_expl = None
         self._has_reach = self._has_ev = False
@@ -220,9 +224,39 @@ class PublicTree:
             self.modes = [nat.STRAT_F32, nat.STRAT_F32]
         self.update_reach_probs()
 
-    def fill_with_agent_policy(self, agent):
-        """StrategyFiller._fill_with_agent_policy (:88-116): query the agent at every decision node."""
+    def decision_nodes(self):
+        """flat ids of the decision nodes in flat order = the batch order of EvalAgentBase.get_a_probs_for_public_tree"""
         ft = self.flat
+        return np.nonzero((ft.kind <= KIND_P1) & (ft.first_child >= 0))[0]
+
+    def fill_with_agent_policy(self, agent):
+        """StrategyFiller._fill_with_agent_policy (:88-116).  Agents that answer for the whole tree at once
+        (`get_a_probs_for_public_tree(tree)` -> device float32 [n_decision, R, N_ACTIONS]) are filled by ONE device gather;
+        others are queried node by node like the reference does."""
+        ft = self.flat
+        batched = getattr(agent, "get_a_probs_for_public_tree", None)
+        probs = batched(self) if batched is not None else None
+        if probs is not None:
+            import ctypes as C
+            from pokerrl_b200.solver import _on, _stream
+            dev = self.dtree.device
+            probs = torch.as_tensor(probs).to(device=dev, dtype=torch.float32).contiguous()
+            dec = self.decision_nodes()
+            assert probs.shape[0] == dec.size and probs.shape[1] == ft.R, probs.shape
+            if getattr(self, "_slot_maps", None) is None:
+                dec_idx = np.full(ft.n_nodes, -1, np.int64)
+                dec_idx[dec] = np.arange(dec.size)
+                child = np.nonzero(ft.slot >= 0)[0]  # flat order == slot order
+                self._slot_maps = (torch.from_numpy(dec_idx[ft.parent[child]].astype(np.int32)).to(dev),
+                                   torch.from_numpy(ft.action[child].astype(np.int32)).to(dev))
+            d_of, a_of = self._slot_maps
+            with _on(dev):
+                nat.call("prl_gather_agent_policy", C.c_void_p(probs.data_ptr()), int(probs.shape[2]), C.c_void_p(d_of.data_ptr()),
+                         C.c_void_p(a_of.data_ptr()), ft.n_slots, ft.R, self.dtree.ld, C.c_void_p(self.bufs.strat.data_ptr()),
+                         _stream(dev))
+            self.modes = [nat.STRAT_F32, nat.STRAT_F32]
+            self.update_reach_probs()
+            return
         rows, dt = np.zeros((ft.n_slots, ft.R)), None
         for n in np.nonzero((ft.kind <= KIND_P1) & (ft.first_child >= 0))[0]:
             node = NodeView(self, n)

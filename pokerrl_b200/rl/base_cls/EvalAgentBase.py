@@ -24,6 +24,13 @@ class EvalAgentBase:
     def get_a_probs_for_each_hand(self):
         raise NotImplementedError
 
+    def get_a_probs_for_public_tree(self, tree):
+        """Optional batched form of the query loop of StrategyFiller._fill_with_agent_policy (:88-116): action
+        probabilities of EVERY decision node of `tree` at once, float32 [n_decision, RANGE_SIZE, N_ACTIONS] in the order of
+        `tree.decision_nodes()` (a torch tensor, ideally already on the tree's device).  Return None (default) to be queried
+        node by node through set_to_public_tree_node_state / get_a_probs_for_each_hand."""
+        return None
+
     def can_compute_mode(self):
         raise NotImplementedError
 

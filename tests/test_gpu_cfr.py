@@ -166,3 +166,48 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
     assert b.iter_counter == 10
     assert b.solvers[0].exploitability_current() == g["curr_series"][10, 1]
     assert b.solvers[0].exploitability_average() == g["avg_series"][9, 1]
+
+
+def test_batched_fill_with_agent_policy_equals_the_per_node_loop():
+    """N2 (SURVEY.md §8f): the agent answers for all decision nodes at once and one device gather fills the strategy table;
+    same table, same exploitability as the reference-style node-by-node query loop (StrategyFiller.py:88-116) - NL-Leduc and
+    a 32-board Flop5Holdem tree."""
+    import torch
+    from pokerrl_b200.cfr.TabularCFREvalAgent import TabularCFREvalAgent
+    from pokerrl_b200.game.PublicTree import PublicTree
+    from pokerrl_b200.game.flat_tree import FlatTree
+    from pokerrl_b200.game.games import DiscretizedNLLeduc, Flop5Holdem
+    from pokerrl_b200.game.wrappers import HistoryEnvBuilder
+    from pokerrl_b200.rl.base_cls.TrainingProfileBase import TrainingProfileBase
+    from pokerrl_b200.solver import CFRSolver
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from twocard_common import random_board_spec
+    for game, bet_set, spec in ((DiscretizedNLLeduc, bet_sets.POT_ONLY, None), (Flop5Holdem, [1.0], random_board_spec(32, 4))):
+        args = game.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[game.DEFAULT_STACK_SIZE] * 2,
+                             bet_sizes_list_as_frac_of_pot=list(bet_set))
+        ft = FlatTree(game, args, board_spec=spec)
+        os.environ["PRL_ENGINE"] = "levels"
+        try:
+            s = CFRSolver(ft, "CFRPlus")
+            s.iteration(5)
+        finally:
+            os.environ.pop("PRL_ENGINE", None)
+        t_prof = TrainingProfileBase(name="n2", game_cls=game, agent_bet_set=list(bet_set), eval_stack_sizes=None)
+        agent = TabularCFREvalAgent(t_prof=t_prof)
+        from pokerrl_b200.cfr.TabularCFREvalAgent import average_strategy_table, tree_fingerprint
+        agent.update_weights((average_strategy_table(s), tree_fingerprint(ft)))
+        bldr = HistoryEnvBuilder(env_cls=game, env_args=args)
+        trees = []
+        for batched in (True, False):
+            tree = PublicTree(env_bldr=bldr, stack_size=args.starting_stack_sizes_list, stop_at_street=None, board_spec=spec)
+            tree.build_tree()
+            if not batched:
+                agent.get_a_probs_for_public_tree = lambda tree: None
+            tree.fill_with_agent_policy(agent=agent)
+            tree.compute_ev()
+            trees.append(tree)
+        assert torch.equal(trees[0].bufs.strat, trees[1].bufs.strat)
+        assert np.array_equal(trees[0].root.exploitability, trees[1].root.exploitability)
+        assert abs(float(np.mean(trees[0].root.exploitability)) * game.EV_NORMALIZER - s.exploitability_average()) <= \
+            1e-5 * s.exploitability_average()
