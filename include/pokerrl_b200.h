@@ -241,8 +241,9 @@ typedef struct {
     float* regret;           /* DEVICE float[n_rows][ldb] */
     float* avg;              /* DEVICE float[n_rows][ldb]  CFR+ average strategy */
     int64_t* w_private;      /* DEVICE int64[grid][2][n_range] scratch */
-    int64_t* w_total;        /* DEVICE int64[2][n_range]: fixed-point sums over this device's boards of board_mult * root
-                                value (array 0: ev, array 1: ev_br), natural hand order */
+    int64_t* w_total;        /* DEVICE int64[4][n_range]: fixed-point sums over this device's boards of board_mult * root value,
+                                natural hand order.  Update sweep: array 0 = ev of the seat; evaluation sweep of seat p:
+                                arrays 2p = ev, 2p + 1 = ev_br */
 } prl_board_game_t;
 
 /* out[8] = {n_live, ldb, blob bytes per board, byte offset of the int16 hand ids, byte offset of the card rows,
@@ -258,7 +259,7 @@ int prl_board_build_tables(const int32_t* ranks, const uint64_t* board_mask, con
 /* One sweep over all boards for seat p.  eval == 0: CFR+ update of p's post-deal rows (iteration iter, averaging delay
  * `delay`); eval != 0: values and best-response values of p with the strategies of p / the opponent taken from
  * src_own / src_opp (0 = regret matching of `regret`, 1 = rows of `avg`).  trunk_reach_opp = DEVICE float[ld]: reach row
- * of the opponent at the chance node.  Leaves the fixed-point sums in g->w_total (zeroed first). */
+ * of the opponent at the chance node.  Leaves the fixed-point sums in g->w_total (the arrays it produces are zeroed first). */
 int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int src_own, int src_opp, const float* trunk_reach_opp,
                     int iter, int delay, prl_stream_t stream);
 
@@ -266,6 +267,29 @@ int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int src_own, int
  * a < n_arr: the chance node's rows for the trunk sweep (after an all-reduce of w_total across GPUs, if sharded). */
 int prl_board_collect(const prl_board_game_t* g, int n_arr, const int16_t* sym_perm, int n_sym, float* out, int ld,
                       prl_stream_t stream);
+
+/* The pre-deal trunk (<= 8 nodes, breadth-first ids = flat-tree ids 0 .. n_nodes - 1; exactly one chance node, a leaf here)
+ * for prl_board_trunk: one launch replaces the level sweeps over the trunk - ValueFiller.py:64-125 bottom-up from the
+ * chance node's sums, CFRPlus.py:37-87 at seat p's nodes, StrategyFiller.py:118-146 for p's reach rows (update form), or
+ * values + best response of both seats and the root exploitability (evaluation form, out_expl = DEVICE float[2]). */
+typedef struct {
+    int32_t n_nodes, chance_node, n_buf_nodes, ld, n_range;
+    int32_t mode[2];        /* PRL_STRAT_* source of each seat's trunk strategy (UNIFORM64, F32 or AVG_F32) */
+    float eq_const;
+    int8_t kind[8], first_child[8], n_children[8], acted_last[8];
+    int32_t first_slot[8];
+    float pot[8];
+    const int8_t* hand_cards; /* DEVICE int8[n_range][2] */
+    float* reach;   /* DEVICE float[2][n_buf_nodes][ld] */
+    float* ev;
+    float* ev_br;
+    float* regret;  /* DEVICE float[n_slots][ld] trunk tables (natural hand order) */
+    float* strat;
+    float* avg;
+} prl_trunk_t;
+
+int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, int eval, int p, int n_sym, const int16_t* sym_perm, int iter,
+                    int delay, float* out_expl, prl_stream_t stream);
 
 /* Strength-ordered rows <-> natural-order rows.  row_src / row_dst = DEVICE int64[rows_per_board][2] {row on board 0,
  * stride per board} in the strength-ordered table and in a natural-order table of stride ld. */

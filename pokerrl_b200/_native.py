@@ -50,6 +50,14 @@ class PrlBoardGame(C.Structure):
                 ("avg", C.c_void_p), ("w_private", C.c_void_p), ("w_total", C.c_void_p)]
 
 
+class PrlTrunk(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("chance_node", C.c_int32), ("n_buf_nodes", C.c_int32), ("ld", C.c_int32),
+                ("n_range", C.c_int32), ("mode", C.c_int32 * 2), ("eq_const", C.c_float),
+                ("kind", C.c_int8 * 8), ("first_child", C.c_int8 * 8), ("n_children", C.c_int8 * 8), ("acted_last", C.c_int8 * 8),
+                ("first_slot", C.c_int32 * 8), ("pot", C.c_float * 8), ("hand_cards", C.c_void_p), ("reach", C.c_void_p),
+                ("ev", C.c_void_p), ("ev_br", C.c_void_p), ("regret", C.c_void_p), ("strat", C.c_void_p), ("avg", C.c_void_p)]
+
+
 class PrlEnvCfg(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int32), ("kind", C.c_int32), ("n_actions", C.c_int32), ("n_rounds", C.c_int32),
@@ -121,6 +129,9 @@ def lib():
     L.prl_board_collect.argtypes = [gp, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.prl_board_permute.argtypes = [gp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p]
+    L.prl_board_trunk.argtypes = [gp, C.POINTER(PrlTrunk), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p]
+    L.prl_board_trunk.restype = C.c_int
     for f in ("prl_board_layout", "prl_board_grid", "prl_board_shape_ok", "prl_board_build_tables", "prl_board_sweep",
               "prl_board_collect", "prl_board_permute"):
         getattr(L, f).restype = C.c_int

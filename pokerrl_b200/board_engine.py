@@ -162,9 +162,12 @@ class BoardCFRSolver:
         g.tables, g.board_prob, g.board_mult = self.t_blob.data_ptr(), self.t_prob.data_ptr(), self.t_mult.data_ptr()
         g.regret, g.avg = self.regret.data_ptr(), self.avg.data_ptr()
         self.w_private = torch.zeros((g.grid, 2, self.R), dtype=torch.int64, device=dev)
-        self.w_total = torch.zeros((2, self.R), dtype=torch.int64, device=dev)
+        self.w_total = torch.zeros((4, self.R), dtype=torch.int64, device=dev)
         g.w_private, g.w_total = self.w_private.data_ptr(), self.w_total.data_ptr()
         self.g = g
+        # the trunk in one launch (prl_board_trunk); PRL_TRUNK=levels keeps the level-kernel chain (A/B, cross-check)
+        self.fused_trunk = os.environ.get("PRL_TRUNK", "fused") != "levels"
+        self._expl = torch.zeros(2, dtype=torch.float32, device=dev)
         # where the level kernels expect the chance node's sums: prl_value_levels(chance_phase 1 / 2), one chance node,
         # one chunk -> W[arr] at float offset (4 + arr) * ld of the workspace
         self._w_off = 4 * self.ld
@@ -173,6 +176,35 @@ class BoardCFRSolver:
                           + self.n_boards_total * len(dec))
 
     # ------------------------------------------------------------------------------------------------ helpers
+    def _trunk_desc(self, bufs, modes):
+        ft, t = self.ft1, nat.PrlTrunk()
+        n = self.chance_node + 1
+        assert n <= 8 and int(ft.level_start[self.chance_level + 1]) == n, "the trunk must be the first nodes of the flat tree"
+        t.n_nodes, t.chance_node, t.n_buf_nodes, t.ld, t.n_range = n, self.chance_node, self.trunk.n_nodes, self.ld, self.R
+        t.mode[0], t.mode[1] = modes
+        t.eq_const = self.g.eq_const
+        for i in range(n):
+            t.kind[i], t.first_child[i], t.n_children[i] = int(ft.kind[i]), int(ft.first_child[i]), int(ft.n_children[i])
+            t.acted_last[i], t.pot[i] = int(ft.acted_last[i]), float(ft.pot[i])
+            t.first_slot[i] = int(ft.first_slot[i]) if ft.first_slot[i] >= 0 else 0
+        t.hand_cards = self.trunk.t_hand_cards.data_ptr()
+        t.reach, t.ev, t.ev_br = bufs.reach.data_ptr(), bufs.ev.data_ptr(), bufs.ev_br.data_ptr()
+        t.regret, t.strat, t.avg = bufs.regret.data_ptr(), bufs.strat.data_ptr(), bufs.avg.data_ptr()
+        return t
+
+    def _trunk(self, bufs, modes, evaluate, p):
+        nat.call("prl_board_trunk", C.byref(self.g), C.byref(self._trunk_desc(bufs, modes)), int(evaluate), p, self.n_sym,
+                 C.c_void_p(self.t_sym.data_ptr()) if self.n_sym else None, self.iter_counter, self.delay,
+                 C.c_void_p(self._expl.data_ptr()), _stream(self.device))
+
+    def _reduce(self, view):
+        if self._reduce_fn is not None:
+            self._reduce_fn(view)
+        elif self.world > 1:  # the ONE collective of the path; int64 sums are exact in any order
+            import torch.distributed as dist
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        self.n_allreduce += 1
+
     def _trunk_reach_row(self, bufs, seat):
         return C.c_void_p(bufs.reach.data_ptr() + 4 * (seat * self.trunk.n_nodes + self.chance_node) * self.ld)
 
@@ -189,15 +221,16 @@ class BoardCFRSolver:
                  self.iter_counter, self.delay, _stream(self.device))
 
     def _sweep_end(self, bufs, p, evaluate):
+        """level-kernel trunk path: cross-rank sum, then the chance node's rows into the level kernels' workspace"""
         n_arr = 2 if evaluate else 1
-        if self._reduce_fn is not None:
-            self._reduce_fn(self.w_total[:n_arr])
-        elif self.world > 1:  # the ONE collective of the path; int64 sums are exact in any order
-            import torch.distributed as dist
-            dist.all_reduce(self.w_total[:n_arr], op=dist.ReduceOp.SUM, group=self.group)
-        self.n_allreduce += 1
+        view = self.w_total[2 * p:2 * p + 2] if evaluate else self.w_total[:1]
+        self._reduce(view)
         out = bufs.workspace.data_ptr() + 4 * (self._w_off + 2 * p * self.ld)
-        nat.call("prl_board_collect", C.byref(self.g), n_arr, C.c_void_p(self.t_sym.data_ptr()) if self.n_sym else None,
+        g2 = self.g
+        if evaluate and p == 1:  # collect reads w_total from its start: point it at this seat's arrays
+            g2 = nat.PrlBoardGame.from_buffer_copy(self.g)
+            g2.w_total = self.w_total.data_ptr() + 8 * 2 * self.R
+        nat.call("prl_board_collect", C.byref(g2), n_arr, C.c_void_p(self.t_sym.data_ptr()) if self.n_sym else None,
                  self.n_sym, C.c_void_p(out), self.ld, _stream(self.device))
 
     def _sweep(self, bufs, p, evaluate, src_own, src_opp):
@@ -205,14 +238,20 @@ class BoardCFRSolver:
         self._sweep_end(bufs, p, evaluate)
 
     def _update_begin(self, p):
-        """first half of seat p's half-iteration: trunk terminals of the chance level, then the board sweep"""
+        """first half of seat p's half-iteration: the board sweep (level path: the chance level's trunk terminals first)"""
         cl = self.chance_level
-        self._levels(self.bufs, 1 << p, False, self.algo, p, self.modes, cl, cl, 1)
+        if not self.fused_trunk:
+            self._levels(self.bufs, 1 << p, False, self.algo, p, self.modes, cl, cl, 1)
         self._sweep_begin(self.bufs, p, False, SRC_REGRET, SRC_REGRET)
 
     def _update_end(self, p):
         """second half: cross-rank sum, chance node row, trunk regrets / matching / averaging, trunk reach of p"""
         cl = self.chance_level
+        if self.fused_trunk:
+            self._reduce(self.w_total[:1])
+            self._trunk(self.bufs, self.modes, False, p)
+            self.modes[p] = nat.STRAT_F32
+            return
         self._sweep_end(self.bufs, p, False)
         self._levels(self.bufs, 1 << p, False, self.algo, p, self.modes, cl, cl, 2)
         if cl > 0:
@@ -239,6 +278,13 @@ class BoardCFRSolver:
 
     def _evaluate(self, bufs, modes, src):
         cl = self.chance_level
+        if self.fused_trunk:
+            for p in (0, 1):
+                self._sweep_begin(bufs, p, True, src, src)
+            self._reduce(self.w_total)
+            self._trunk(bufs, modes, True, -1)
+            e = self._expl.cpu().numpy()
+            return sum(float(e[p]) * self.ev_normalizer for p in range(2)) / 2
         self._levels(bufs, 3, True, -1, -1, modes, cl, cl, 1)
         for p in (0, 1):
             self._sweep(bufs, p, True, src, src)

@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     }
     // merge into the device-wide sums (integer adds: exact in any order)
     __syncthreads();
-    unsigned long long* wt = reinterpret_cast<unsigned long long*>(G.w_total);
+    unsigned long long* wt = reinterpret_cast<unsigned long long*>(G.w_total) + (EVAL ? 2 * P * kRange : 0);  // eval: [seat][ev, ev_br]
     for (int h = tid; h < (EVAL ? 2 : 1) * kRange; h += kThreads) {
         const long long v = wp[h];
         if (v != 0) atomicAdd(wt + h, (unsigned long long)v);
@@ -657,6 +657,164 @@ __global__ void board_permute_kernel(const unsigned char* __restrict__ tables, i
     }
 }
 
+// =====================================================================================================================
+// The pre-deal trunk in ONE launch (one CTA): chance-node rows from the fixed-point sums (integer sum over the suit
+// permutations), fold terminals, value backup, and - update form - regrets / matching / average of seat p's trunk nodes and
+// its new reach rows; evaluation form: values + best response of both seats and the root exploitability.  Same statements as
+// the level kernels (ValueFiller.py:64-125, CFRPlus.py:37-87, StrategyFiller.py:118-146) on <= 8 nodes in natural hand order.
+// =====================================================================================================================
+constexpr int kTrunkThreads = 1024;
+
+__device__ __forceinline__ float trunk_sigma(const prl_trunk_t& t, int src, int slot, int A, int h) {
+    if (src == PRL_STRAT_UNIFORM64) return 1.0f / (float)A;
+    const float* tab = (src == PRL_STRAT_F32) ? t.strat : t.avg;
+    return tab[(size_t)slot * t.ld + h];
+}
+
+template <bool EVAL>
+__global__ void __launch_bounds__(kTrunkThreads) trunk_kernel(const prl_trunk_t t, const long long* __restrict__ w_total,
+                                                              const int16_t* __restrict__ sym_perm, int n_sym, double inv_scale,
+                                                              int p_upd, int iter, int delay, float m_old, float m_new, float* out_expl) {
+    __shared__ float ro[kRange + 2];
+    __shared__ float cs[64];
+    __shared__ float red[32];
+    __shared__ double dred[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t N = (size_t)t.n_buf_nodes, ld = (size_t)t.ld;
+    const int seat_lo = EVAL ? 0 : p_upd, seat_hi = EVAL ? 1 : p_upd;
+    // 1. the chance node's rows
+    for (int p = seat_lo; p <= seat_hi; ++p)
+        for (int k = 0; k < (EVAL ? 2 : 1); ++k) {
+            const long long* W = w_total + (size_t)(EVAL ? (2 * p + k) : 0) * kRange;
+            float* dst = (k ? t.ev_br : t.ev) + ((size_t)p * N + t.chance_node) * ld;
+            for (int h = tid; h < kRange; h += kTrunkThreads) {
+                long long s = 0;
+                if (n_sym > 1) {
+                    for (int q = 0; q < n_sym; ++q) s += W[sym_perm[(size_t)q * kRange + h]];
+                } else {
+                    s = W[h];
+                }
+                dst[h] = (float)((double)s * inv_scale);
+            }
+        }
+    // 2. fold terminals (no board): ValueFiller.py:103-113 for two-card hands
+    for (int n = 0; n < t.n_nodes; ++n) {
+        if (t.kind[n] != PRL_KIND_FOLD) continue;
+        for (int p = seat_lo; p <= seat_hi; ++p) {
+            const float* rg = t.reach + ((size_t)(1 - p) * N + n) * ld;
+            __syncthreads();
+            float part = 0.0f;
+            for (int h = tid; h < kRange; h += kTrunkThreads) {
+                const float r = rg[h];
+                ro[h] = r;
+                part += r;
+            }
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) red[warp] = part;
+            __syncthreads();
+            float T = 0.0f;
+            for (int w = 0; w < kTrunkThreads / 32; ++w) T += red[w];
+            if (tid < kDeck) {  // per-card sums over the lexicographic range layout, fixed order
+                float acc = 0.0f;
+                const int c = tid;
+                for (int r = 0; r < c; ++r) acc += ro[r * (2 * kDeck - 1 - r) / 2 + c - r - 1];
+                const int b0 = c * (2 * kDeck - 1 - c) / 2;
+                for (int k = 0; k < kDeck - 1 - c; ++k) acc += ro[b0 + k];
+                cs[c] = acc;
+            }
+            __syncthreads();
+            const float sc = t.eq_const * t.pot[n] * 0.5f * ((t.acted_last[n] == p) ? -1.0f : 1.0f);
+            float* e = t.ev + ((size_t)p * N + n) * ld;
+            float* b = t.ev_br + ((size_t)p * N + n) * ld;
+            for (int h = tid; h < kRange; h += kTrunkThreads) {
+                const float v = (T - cs[t.hand_cards[2 * h]] - cs[t.hand_cards[2 * h + 1]] + ro[h]) * sc;
+                e[h] = v;
+                if (EVAL) b[h] = v;
+            }
+        }
+    }
+    __syncthreads();
+    // 3. decision nodes bottom-up, per hand (children have larger ids); 4. regrets / matching / average; 5. reach of seat p
+    double ex[2] = {0.0, 0.0};
+    for (int h = tid; h < kRange; h += kTrunkThreads) {
+        for (int n = t.n_nodes - 1; n >= 0; --n) {
+            const int k = t.kind[n];
+            if (k > PRL_KIND_P1) continue;
+            const int A = t.n_children[n], fc = t.first_child[n], fs = t.first_slot[n];
+            for (int p = seat_lo; p <= seat_hi; ++p) {
+                float* ev_p = t.ev + (size_t)p * N * ld;
+                float* br_p = t.ev_br + (size_t)p * N * ld;
+                float v = 0.0f, b = 0.0f;
+                if (k != p) {
+                    for (int c = 0; c < A; ++c) v += ev_p[(size_t)(fc + c) * ld + h];
+                    if (EVAL)
+                        for (int c = 0; c < A; ++c) b += br_p[(size_t)(fc + c) * ld + h];
+                } else {
+                    for (int c = 0; c < A; ++c) v += trunk_sigma(t, t.mode[p], fs + c, A, h) * ev_p[(size_t)(fc + c) * ld + h];
+                    if (EVAL) {
+                        b = br_p[(size_t)fc * ld + h];
+                        for (int c = 1; c < A; ++c) b = fmaxf(b, br_p[(size_t)(fc + c) * ld + h]);
+                    } else {  // CFRPlus.py:37-63
+                        float ssum = 0.0f;
+                        for (int c = 0; c < A; ++c) {
+                            float* rg = t.regret + (size_t)(fs + c) * ld + h;
+                            const float r = fmaxf((ev_p[(size_t)(fc + c) * ld + h] - v) + *rg, 0.0f);
+                            *rg = r;
+                            ssum += r;
+                        }
+                        const float inv = (ssum > 0.0f) ? 1.0f / ssum : 0.0f;
+                        for (int c = 0; c < A; ++c) {
+                            const float r = t.regret[(size_t)(fs + c) * ld + h];
+                            t.strat[(size_t)(fs + c) * ld + h] = (ssum > 0.0f) ? r * inv : 1.0f / (float)A;
+                        }
+                    }
+                }
+                ev_p[(size_t)n * ld + h] = v;
+                if (EVAL) br_p[(size_t)n * ld + h] = b;
+            }
+        }
+        if (EVAL) {
+            for (int p = 0; p < 2; ++p)  // ValueFiller.py:95-101 at the root
+                ex[p] += (double)t.reach[((size_t)p * N) * ld + h] *
+                         ((double)t.ev_br[((size_t)p * N) * ld + h] - (double)t.ev[((size_t)p * N) * ld + h]);
+        } else {
+            const int p = p_upd;
+            float* rp = t.reach + (size_t)p * N * ld;
+            for (int n = 0; n < t.n_nodes; ++n) {  // StrategyFiller.py:118-146 with the new strategy; average CFRPlus.py:65-87
+                const int k = t.kind[n];
+                if (k > PRL_KIND_P1) continue;
+                const int A = t.n_children[n], fc = t.first_child[n], fs = t.first_slot[n];
+                const float r = rp[(size_t)n * ld + h];
+                for (int c = 0; c < A; ++c) {
+                    float s = 1.0f;
+                    if (k == p) {
+                        s = t.strat[(size_t)(fs + c) * ld + h];
+                        if (iter >= delay) {
+                            float* a = t.avg + (size_t)(fs + c) * ld + h;
+                            *a = m_old * (*a) + m_new * s;
+                        }
+                    }
+                    rp[(size_t)(fc + c) * ld + h] = s * r;
+                }
+            }
+        }
+    }
+    if (EVAL) {
+        for (int p = 0; p < 2; ++p) {
+            double v = ex[p];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if (lane == 0) dred[warp] = v;
+            __syncthreads();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int w = 0; w < kTrunkThreads / 32; ++w) s += dred[w];
+                out_expl[p] = (float)s;
+            }
+        }
+    }
+}
+
 bool shape_matches(const prl_board_game_t* g) {
     if (g->n_local != ShapeFHP::N) return false;
     for (int i = 0; i < ShapeFHP::N; ++i)
@@ -754,7 +912,10 @@ extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int s
         const bool folder = n < g->n_local && g->kind[n] == PRL_KIND_FOLD && g->acted_last[n] == p;
         a.sc[n] = (n < g->n_local) ? g->eq_const * g->pot[n] * 0.5f * (folder ? -1.0f : 1.0f) : 0.0f;
     }
-    if (int e = prl::check(cudaMemsetAsync(g->w_total, 0, sizeof(long long) * 2 * kRange, s), "prl_board_sweep: memset")) return e;
+    {   // the sums this launch produces: update -> w_total[0]; evaluation of seat p -> w_total[2p], w_total[2p + 1]
+        char* base = reinterpret_cast<char*>(g->w_total) + (eval ? sizeof(long long) * 2 * p * kRange : 0);
+        if (int e = prl::check(cudaMemsetAsync(base, 0, sizeof(long long) * (eval ? 2 : 1) * kRange, s), "prl_board_sweep: memset")) return e;
+    }
     int rc;
     if (eval) rc = (p == 0) ? launch_sweep<0, true>(a, grid, s) : launch_sweep<1, true>(a, grid, s);
     else rc = (p == 0) ? launch_sweep<0, false>(a, grid, s) : launch_sweep<1, false>(a, grid, s);
@@ -764,7 +925,7 @@ extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int s
 
 extern "C" int prl_board_collect(const prl_board_game_t* g, int n_arr, const int16_t* sym_perm, int n_sym, float* out, int ld,
                                  prl_stream_t stream) {
-    if (!g || n_arr < 1 || n_arr > 2) return prl::fail("prl_board_collect: bad arguments");
+    if (!g || n_arr < 1 || n_arr > 4) return prl::fail("prl_board_collect: bad arguments");
     board_collect_kernel<<<(kRange + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const long long*>(g->w_total), n_arr, sym_perm, n_sym, 1.0 / (double)(1ull << g->frac_bits), out, ld);
     prl::count_launch();
@@ -778,4 +939,24 @@ extern "C" int prl_board_permute(const prl_board_game_t* g, int rows_per_board, 
         (const unsigned char*)g->tables, g->n_boards, rows_per_board, row_src, row_dst, sorted_tab, natural_tab, ld, to_natural);
     prl::count_launch();
     return prl::check(cudaGetLastError(), "prl_board_permute");
+}
+
+// Trunk of seat p's half-iteration (eval == 0) or of an evaluation of both seats (eval != 0) in one launch; see prl_trunk_t.
+extern "C" int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, int eval, int p, int n_sym, const int16_t* sym_perm,
+                               int iter, int delay, float* out_expl, prl_stream_t stream) {
+    if (!g || !t || t->n_nodes < 1 || t->n_nodes > 8) return prl::fail("prl_board_trunk: 1..8 trunk nodes");
+    if (t->n_range != kRange || g->n_deck != kDeck) return prl::fail("prl_board_trunk: 52-card deck / 1326 hands only");
+    if (eval && !out_expl) return prl::fail("prl_board_trunk: out_expl missing");
+    for (int n = 0; n < t->n_nodes; ++n)
+        if (t->kind[n] == PRL_KIND_SHOWDOWN || t->kind[n] == PRL_KIND_SHOWDOWN_ALLIN)
+            return prl::fail("prl_board_trunk: showdowns before the deal are not supported");
+    const double cw = 0.5 * ((double)iter * (iter + 1) - (double)delay * (delay + 1));  // CFRPlus.py:68-73
+    const double nw = (double)iter - delay + 1;
+    const float m_old = (iter > delay) ? (float)(cw / (cw + nw)) : 0.0f, m_new = (iter > delay) ? (float)(nw / (cw + nw)) : 1.0f;
+    const double inv_scale = 1.0 / (double)(1ull << g->frac_bits);
+    const long long* w = reinterpret_cast<const long long*>(g->w_total);
+    if (eval) trunk_kernel<true><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, sym_perm, n_sym, inv_scale, -1, iter, delay, m_old, m_new, out_expl);
+    else trunk_kernel<false><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, sym_perm, n_sym, inv_scale, p, iter, delay, m_old, m_new, out_expl);
+    prl::count_launch();
+    return prl::check(cudaGetLastError(), "prl_board_trunk");
 }

@@ -107,7 +107,7 @@ def test_root_rows_against_reference_anchored_golden_rows():
             s.t_mult[b] = 1.0
             nat.call("prl_board_sweep", C.byref(s.g), p, 1, 0, 0, C.c_void_p(row.data_ptr()), 0, 0,
                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
-            got = s.w_total[0].cpu().numpy().astype(np.float64) / 2.0 ** s.g.frac_bits
+            got = s.w_total[2 * p].cpu().numpy().astype(np.float64) / 2.0 ** s.g.frac_bits  # evaluation of seat p: arrays 2p, 2p + 1
             ref = (coef_sd * GOLD["showdown"][b] + coef_fold * GOLD["fold"][b]) * 2.0 ** -10
             err = _rel(got, ref)
             worst[p] = max(worst[p], err)
@@ -249,3 +249,23 @@ def test_shards_reproduce_the_single_device_run_bit_for_bit():
         assert torch.equal(e.avg.view(e.n_boards, rpb, ldb), full_avg[r::2])
     for e in parts:
         assert torch.equal(e.bufs.regret, one.bufs.regret) and torch.equal(e.bufs.avg, one.bufs.avg)
+
+
+def test_single_launch_trunk_equals_the_level_kernel_trunk(monkeypatch):
+    """prl_board_trunk (one launch for the pre-deal trunk) against the level kernels driving the same trunk: same regrets
+    and exploitability up to the summation order of the fold terminals' card sums"""
+    spec = random_board_spec(24, 12)
+    a = _engine(spec)
+    monkeypatch.setenv("PRL_TRUNK", "levels")
+    b = _engine(spec)
+    monkeypatch.delenv("PRL_TRUNK")
+    assert a.fused_trunk and not b.fused_trunk
+    for t in range(3):
+        x, y = a.exploitability_current(), b.exploitability_current()
+        assert abs(x - y) <= 2e-6 * abs(y), (t, x, y)
+        a.iteration(1)
+        b.iteration(1)
+        ra, rb = a.bufs.regret.cpu().numpy().astype(np.float64), b.bufs.regret.cpu().numpy().astype(np.float64)
+        assert _rel(ra[:4], rb[:4]) <= 2e-6, t
+        x, y = a.exploitability_average(), b.exploitability_average()
+        assert abs(x - y) <= 1e-4 * abs(y), (t, x, y)

@@ -76,7 +76,7 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     import ctypes as C
     import subprocess
     from pokerrl_b200 import _native
-    pairs = [("prl_tree_t", _native.PrlTree), ("prl_buffers_t", _native.PrlBuffers), ("prl_env_cfg_t", _native.PrlEnvCfg), ("prl_board_game_t", _native.PrlBoardGame)]
+    pairs = [("prl_tree_t", _native.PrlTree), ("prl_buffers_t", _native.PrlBuffers), ("prl_env_cfg_t", _native.PrlEnvCfg), ("prl_board_game_t", _native.PrlBoardGame), ("prl_trunk_t", _native.PrlTrunk)]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "pokerrl_b200.h"', 'int main(void) {']
     for cname, cls in pairs:
         src.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
