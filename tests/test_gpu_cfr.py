@@ -180,8 +180,8 @@ def test_batched_fill_with_agent_policy_equals_the_per_node_loop():
     from pokerrl_b200.game.wrappers import HistoryEnvBuilder
     from pokerrl_b200.rl.base_cls.TrainingProfileBase import TrainingProfileBase
     from pokerrl_b200.solver import CFRSolver
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from pokerrl_b200.game import bet_sets
+    import os
     from twocard_common import random_board_spec
     for game, bet_set, spec in ((DiscretizedNLLeduc, bet_sets.POT_ONLY, None), (Flop5Holdem, [1.0], random_board_spec(32, 4))):
         args = game.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[game.DEFAULT_STACK_SIZE] * 2,
