@@ -175,7 +175,13 @@ __device__ __forceinline__ void node_strategy(const float (&g)[A], int src, floa
         sum += s[a];
     }
     const bool pos = sum > 0.0f;
-    const float inv = pos ? __frcp_rn(sum) : 0.0f;  // correctly rounded reciprocal, no slow-path branch
+    // reciprocal = MUFU.RCP + one Newton step (<= 1 ulp, no range-check branch; sums below 1e-37 cannot occur: regrets are
+    // chip amounts times probabilities)
+    const float sm = fmaxf(sum, 1e-37f);
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sm));
+    inv = fmaf(inv, fmaf(-sm, inv, 1.0f), inv);
+    inv = pos ? inv : 0.0f;
     const float uni = pos ? 0.0f : 1.0f / (float)A;  // CFRPlus.py:53-58: uniform where no regret is positive
 #pragma unroll
     for (int a = 0; a < A; ++a) s[a] = fmaf(s[a], inv, uni);
@@ -246,6 +252,21 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         prefetch_rows(j);
     }
 
+    // P1 inputs of the thread's three strength positions (opponent rows + trunk reach), requested one unit ahead
+    float p1_g[kPerThread][NOPP], p1_x0[kPerThread];
+    auto p1_load = [&](int jj, const int16_t* sh_jj) {
+        const float* rows = tab_opp + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb + tid;
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            const int i = tid + k * kThreads;
+            if (i < kLive) {
+#pragma unroll
+                for (int r = 0; r < NOPP; ++r) p1_g[k][r] = ld_stream(rows + (size_t)r * kLdb + k * kThreads);
+                p1_x0[k] = __ldg(a.trunk_reach_opp + sh_jj[i]);
+            }
+        }
+    };
+
     for (int it = 0; j < nb; j += gridDim.x, ++it) {
         const int buf = it & 1;
         const unsigned char* blob = smem + kBlobOff + buf * kBlobA;
@@ -258,29 +279,21 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             prefetch_rows(jn);
         }
         const float prob = __ldg(G.board_prob + j);
-        const float* opp_rows = tab_opp + (size_t)j * kBoardFloats + (size_t)OPP0 * kLdb + tid;
-        mbar_wait(&bars[buf], (it >> 1) & 1);
+        if (it == 0) {
+            mbar_wait(&bars[buf], 0);
+            p1_load(j, sh);
+        }
 
         // ------------------------------------------------------------------------------------------ P1: reach, top-down
         // x[i] = reach of the OPPONENT at local node i (StrategyFiller.py:118-146); terminal rows go to S in strength order.
-        // All loads of the thread's three strength positions are in flight together.
+        // The rows were requested before the previous unit's last barrier (p1_load): their latency is off this path.
         {
-            float g[kPerThread][NOPP], x0[kPerThread];
-#pragma unroll
-            for (int k = 0; k < kPerThread; ++k) {
-                const int i = tid + k * kThreads;
-                if (i < kLive) {
-#pragma unroll
-                    for (int r = 0; r < NOPP; ++r) g[k][r] = ld_stream(opp_rows + (size_t)r * kLdb + k * kThreads);
-                    x0[k] = __ldg(a.trunk_reach_opp + sh[i]);
-                }
-            }
 #pragma unroll
             for (int k = 0; k < kPerThread; ++k) {
                 const int i = tid + k * kThreads;
                 if (i < kLive) {
                     float x[SH::N];
-                    x[0] = x0[k] * prob;  // the deal (StrategyFiller.py:137-140); blocked hands are not stored at all
+                    x[0] = p1_x0[k] * prob;  // the deal (StrategyFiller.py:137-140); blocked hands are not stored at all
                     static_for<0, SH::N>([&](auto I) {
                         constexpr int n = decltype(I)::value;
                         constexpr int A = SH::n_children(n);
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                             if constexpr (SH::kind(n) == OPP) {
                                 float gg[A], s[A];
 #pragma unroll
-                                for (int c = 0; c < A; ++c) gg[c] = g[k][SH::row_of(fc + c) - OPP0];
+                                for (int c = 0; c < A; ++c) gg[c] = p1_g[k][SH::row_of(fc + c) - OPP0];
                                 node_strategy<A>(gg, EVAL ? a.src_opp : 0, s);
 #pragma unroll
                                 for (int c = 0; c < A; ++c) x[fc + c] = x[n] * s[c];
@@ -386,6 +399,26 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 if (lane == 31) wsum[v * 16 + warp] = incw;
             }
         }
+        // P3 inputs of the first strength position: requested here, consumed after the prefix sums are written back
+        const float mult = __ldg(G.board_mult + j);
+        const double fx = (double)mult * a.fx_scale;
+        const float* own_rows = tab_own + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
+        float* reg_rows = G.regret + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
+        float* avg_rows = G.avg + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
+        float gA[NOWN], aA[NOWN], gB[NOWN], aB[NOWN];
+        auto p3_load = [&](int k, float (&g)[NOWN], float (&av)[NOWN]) {
+            if (tid + k * kThreads < kLive) {
+#pragma unroll
+                for (int r = 0; r < NOWN; ++r) g[r] = ld_stream(own_rows + (size_t)r * kLdb + k * kThreads);
+            }
+#pragma unroll
+            for (int r = 0; r < NOWN; ++r) av[r] = 0.0f;
+            if (read_avg && tid + k * kThreads < kLive) {
+#pragma unroll
+                for (int r = 0; r < NOWN; ++r) av[r] = ld_stream(avg_rows + (size_t)r * kLdb + k * kThreads);
+            }
+        };
+        p3_load(0, gA, aA);
         __syncthreads();  // B2: card rows done, S may be overwritten, the row table may be replaced
         if (tid == 0 && jn < nb) {
             mbar_expect_tx(&bars[2], kRowIdxBytes);
@@ -434,26 +467,8 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         __syncthreads();  // B4: prefix arrays complete
 
         // ------------------------------------------------------------------------------------------ P3: values, bottom-up
-        const float mult = __ldg(G.board_mult + j);
-        const double fx = (double)mult * a.fx_scale;
-        const float* own_rows = tab_own + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
-        float* reg_rows = G.regret + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
-        float* avg_rows = G.avg + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
-#pragma unroll 1
-        for (int k = 0; k < kPerThread; ++k) {
+        auto p3_hand = [&](int k, const float (&gown)[NOWN], const float (&av)[NOWN]) {
             const int i = tid + k * kThreads;
-            if (i >= kLive) break;
-            // the seat's rows for this hand, requested before the shared-memory work below
-            float gown[NOWN], av[NOWN];
-#pragma unroll
-            for (int r = 0; r < NOWN; ++r) gown[r] = ld_stream(own_rows + (size_t)r * kLdb + k * kThreads);
-            if (read_avg) {
-#pragma unroll
-                for (int r = 0; r < NOWN; ++r) av[r] = ld_stream(avg_rows + (size_t)r * kLdb + k * kThreads);
-            } else {
-#pragma unroll
-                for (int r = 0; r < NOWN; ++r) av[r] = 0.0f;
-            }
             const uint64_t w = rec[i];
             const int hand = sh[i];
             long long* wacc = wp + hand;
@@ -533,6 +548,18 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             // the board's contribution to its parent's sum (ValueFiller.py:76-78), 64-bit fixed point
             *wacc = w_ev + __double2ll_rn((double)e[0] * fx);
             if constexpr (EVAL) wacc[kRange] = w_br + __double2ll_rn((double)br[0] * fx);
+        };
+        // software pipeline over the thread's three strength positions: the next position's rows are in flight while the
+        // current one is evaluated (position 0 was requested before the prefix sums were written back)
+        p3_load(1, gB, aB);
+        p3_hand(0, gA, aA);
+        p3_load(2, gA, aA);
+        if (tid + kThreads < kLive) p3_hand(1, gB, aB);
+        if (tid + 2 * kThreads < kLive) p3_hand(2, gA, aA);
+        // next unit's P1 inputs: requested before the barrier below, consumed after it (the other table buffer is long there)
+        if (jn < nb) {
+            mbar_wait(&bars[buf ^ 1], ((it + 1) >> 1) & 1);
+            p1_load(jn, reinterpret_cast<const int16_t*>(smem + kBlobOff + (buf ^ 1) * kBlobA + kRecBytes));
         }
         __syncthreads();  // B5: S / Er / tables of this board are free
     }
