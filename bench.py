@@ -294,8 +294,59 @@ def run_aux(a):
     print(json.dumps(out))
 
 
+def converge_fhp(a, rank, world, local_rank):
+    """BASELINE.json metric, second half: mbb/g exploitability vs wall-clock.  CFR+ on the full game; every --eval-every
+    iterations the exact exploitability of the current and of the average strategy is computed (evaluation time is kept
+    apart from solve time: both clocks are reported)."""
+    import torch
+    import torch.distributed as dist
+    from pokerrl_b200.board_engine import BoardCFRSolver
+    from pokerrl_b200.game.holdem_boards import BoardSpec
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    g, args = fhp_args()
+    spec = BoardSpec.full_game(g.RULES)
+    if a.fhp_boards:
+        spec = fhp_subset(spec, a.fhp_boards)
+    s = BoardCFRSolver(g, args, spec, device="cuda:%d" % local_rank, rank=rank, world=world)
+    s.iteration(2)
+    s.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    curve = [{"iteration": 0, "solve_s": 0.0, "wall_s": 0.0, "mbb_per_g_current": s.exploitability_current(), "mbb_per_g_average": None}]
+    solve, t_wall0, it = 0.0, time.perf_counter(), 0
+    while it < a.converge:
+        n = min(a.eval_every, a.converge - it)
+        t0 = time.perf_counter()
+        s.iteration(n)
+        torch.cuda.synchronize()
+        solve += time.perf_counter() - t0
+        it += n
+        cur, avg = s.exploitability_current(), s.exploitability_average()
+        curve.append({"iteration": it, "solve_s": solve, "wall_s": time.perf_counter() - t_wall0, "mbb_per_g_current": cur,
+                      "mbb_per_g_average": avg})
+    if rank == 0:
+        def first_below(x, key):
+            for c in curve[1:]:
+                if c[key] is not None and c[key] <= x:
+                    return {"iteration": c["iteration"], "solve_s": c["solve_s"], "wall_s": c["wall_s"]}
+            return None
+        print(json.dumps({"workload": "Flop5Holdem CFR+ delay 0, %d board classes, range 1326" % spec.boards.shape[0],
+                          "n_gpus": world, "iterations": a.converge, "eval_every": a.eval_every,
+                          "iterations_per_s_solve_only": a.converge / solve,
+                          "time_to_average_strategy_below_mbb_per_g": {str(x): first_below(x, "mbb_per_g_average") for x in (100, 10, 1, 0.1)},
+                          "curve": curve}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main_fhp(a, rank, world, local_rank):
     """BASELINE.json configs[2] (the game the metric is quoted on): Flop5Holdem CFR+ by the board-resident engine."""
+    if a.converge and a.impl != "reference":
+        return converge_fhp(a, rank, world, local_rank)
     N_CLASSES = 134459
     K = a.steps if a.steps is not None else 200
     W = max(3, a.warmup if a.warmup is not None else 5)
@@ -567,6 +618,9 @@ def main():
     ap.add_argument("--fhp-boards", type=int, default=0, help="debug: only the first n isomorphism classes")
     ap.add_argument("--hulh-turns", type=int, default=0, help="hulh: only the first n turn cards (memory: the full 49 need >= 2 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--converge", type=int, default=0, metavar="ITERS",
+                    help="fhp / hulh: run ITERS iterations and print the exploitability-vs-wall-clock curve (one JSON line) "
+                         "instead of the throughput line; evaluation every --eval-every iterations")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

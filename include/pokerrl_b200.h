@@ -309,6 +309,18 @@ int prl_hand_rank_boards(const int8_t* boards, int n_boards, int32_t* out, prl_s
 /* n independent 7-card hands: cards = DEVICE int8[n][7] -> out = DEVICE int32[n] (game_rules.py:219-223 batched). */
 int prl_hand_rank_7(const int8_t* cards, int n, int32_t* out, prl_stream_t stream);
 
+/* Local Best Response roll-out (eval/lbr/LocalLBRWorker.py:377-512, _LBRRolloutManager.get_lbr_checkdown_equity): for each of
+ * n_queries (LBR hand, dealt board cards, agent range) the probability-weighted check-down equity over EVERY completion of
+ * the board.  lbr_hands = DEVICE int8[n][2] (1D cards), boards = DEVICE int8[n][5] (the n_dealt dealt cards first; all
+ * queries of a call are on the same street), ranges = DEVICE float[n][1326] (normalised, zero on hands holding an LBR or
+ * board card), workspace = DEVICE double[prl_lbr_workspace_doubles(n, n_dealt)], out = DEVICE float[n].
+ * first_board_ranks != 0 reproduces a defect of the reference - its board counter `_i` is never advanced
+ * (LocalLBRWorker.py:468-512), so every completion is compared on the ranks of the FIRST completion - and exists for
+ * parity checks against outputs of the reference; 0 (the product's default) ranks every completion on its own cards. */
+long long prl_lbr_workspace_doubles(int n_queries, int n_dealt);
+int prl_lbr_checkdown_equity(const int8_t* lbr_hands, const int8_t* boards, int n_dealt, const float* ranges, int n_queries,
+                             int first_board_ranks, double* workspace, float* out, prl_stream_t stream);
+
 /* Legacy entry points with the exact native signatures the reference binds through ctypes (HOST arrays of row
  * pointers, PokerRL/_/CppWrapper.py:24-27): CppHandeval.py:22-33 and CppLUT.py:22-35 can load this library unchanged.
  * They stage through device memory and run the kernels above (synchronous). */

@@ -118,6 +118,11 @@ def lib():
     L.prl_gather_agent_policy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p]
     L.prl_gather_agent_policy.restype = C.c_int
+    L.prl_lbr_workspace_doubles.argtypes = [C.c_int, C.c_int]
+    L.prl_lbr_workspace_doubles.restype = C.c_longlong
+    L.prl_lbr_checkdown_equity.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
+    L.prl_lbr_checkdown_equity.restype = C.c_int
     gp = C.POINTER(PrlBoardGame)
     L.prl_board_layout.argtypes = [C.POINTER(C.c_int32)]
     L.prl_board_grid.argtypes = []

@@ -24,6 +24,7 @@ SOURCES = {
     "cfr_twocard.cu": [],
     "cfr_board.cu": ["--expt-relaxed-constexpr"],
     "env_kernels.cu": [],
+    "lbr_rollout.cu": [],
 }
 
 
