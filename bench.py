@@ -291,7 +291,7 @@ def run_aux(a):
                                 "sample": "4 000 boards x 1326 hands by oracle/hand_eval_oracle.c (output compared exactly); the "
                                           "reference binary did 2.73 M evals/s on one core (BASELINE.md)"}}
     out["clocks"] = clocks
-    print(json.dumps(out))
+    emit((out))
 
 
 def converge_fhp(a, rank, world, local_rank):
@@ -334,7 +334,7 @@ def converge_fhp(a, rank, world, local_rank):
                 if c[key] is not None and c[key] <= x:
                     return {"iteration": c["iteration"], "solve_s": c["solve_s"], "wall_s": c["wall_s"]}
             return None
-        print(json.dumps({"workload": "Flop5Holdem CFR+ delay 0, %d board classes, range 1326" % spec.boards.shape[0],
+        emit(({"workload": "Flop5Holdem CFR+ delay 0, %d board classes, range 1326" % spec.boards.shape[0],
                           "n_gpus": world, "iterations": a.converge, "eval_every": a.eval_every,
                           "iterations_per_s_solve_only": a.converge / solve,
                           "time_to_average_strategy_below_mbb_per_g": {str(x): first_below(x, "mbb_per_g_average") for x in (100, 10, 1, 0.1)},
@@ -365,7 +365,7 @@ def main_fhp(a, rank, world, local_rank):
                   "board classes: %.4f s/iteration = %.3f it/s on that instance; scaled by the board count (%d / %d; cost is per "
                   "board) to the full game.  The reference itself cannot run Hold'em trees (SURVEY.md headline 2)"
                   % (n_it, threads, FHP_CPU_BOARDS, sec, 1.0 / sec, nb_used, FHP_CPU_BOARDS))
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "CFR+ iterations/s", "value": v, "unit": "iterations/s", "n_gpus": a.gpus, "steps": n_it,
             "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (deterministic game tree, no dataset)", "config": cfg,
@@ -396,6 +396,7 @@ def main_fhp(a, rank, world, local_rank):
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
     L = s.L
+    collective = s.collective
 
     def steps(solver, i0, n):
         out, i = [], i0
@@ -575,8 +576,8 @@ def main_fhp(a, rank, world, local_rank):
         "config": dict(cfg, boards_per_rank=s_n_boards(nb_used, rank, world), engine="board-resident (pokerrl_b200/board_engine.py)",
                        l2="per-rank tables %.1f GB >> 126 MB L2 (no explicit flush)" % (
                            2 * s_n_boards(nb_used, rank, world) * 14 * rows_bytes / 2 ** 30),
-                       parallelism="boards round-robin over %d ranks; per bottom-up sweep ONE all-reduce of the chance node's "
-                                   "int64 fixed-point sums (%d in the timed region)" % (world, n_allreduce)),
+                       parallelism="boards round-robin over %d ranks; per bottom-up sweep ONE cross-rank sum of the chance node's "
+                                   "int64 fixed-point vector (%d in the timed region): %s" % (world, n_allreduce, collective)),
         "clocks": clocks,
         "e2e": {"value": K / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 2 * 8 * (K // a.eval_every) / K,
@@ -598,7 +599,7 @@ def main_fhp(a, rank, world, local_rank):
                                          "classes at %.4f s/iteration, scaled by the board count to the full game (cost is per board); "
                                          "the reference cannot run Hold'em trees at all (SURVEY.md headline 2)"
                                          % (n_it, threads, FHP_CPU_BOARDS, sec)}
-    print(json.dumps(out))
+    emit((out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -607,7 +608,23 @@ def s_n_boards(n, rank, world):
     return len(range(rank, n, world))
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of this process on the real stdout (fd 1 is pointed at stderr while the benchmark runs, so that
+    banners of NCCL / the launcher cannot end up in front of it)"""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj))
+    sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -629,7 +646,7 @@ def main():
         if rank == 0 and a.impl == "b200":
             run_aux(a)
         elif rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "aux workloads carry their CPU baseline in the main line"}))
+            emit(({"impl": "reference", "unavailable": "aux workloads carry their CPU baseline in the main line"}))
         return
     if a.workload == "fhp":
         return main_fhp(a, rank, world, local_rank)
@@ -659,7 +676,7 @@ def main():
             return
         ncpu = os.cpu_count() or 1
         if hulh:
-            print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the hulh sub-game workload (the float64 oracle is "
+            emit(({"impl": "reference", "unavailable": "no CPU arm for the hulh sub-game workload (the float64 oracle is "
                               "exercised on a restricted sub-game in tests/test_gpu_twocard.py)"}))
             return
         if True:
@@ -669,7 +686,7 @@ def main():
             cfg.update(tree=tree_stats(ft))
             v, ms = 1.0 / sec, sec * 1e3
             sample = "%d full CFR+ iterations of the same tree by oracle/cfr_oracle.c (OpenMP)" % K
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "CFR+ iterations/s", "value": v, "unit": "iterations/s", "n_gpus": a.gpus,
             "steps": K, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong" if fhp else "weak", "vs_baseline": None, "dtype": "f64" if fhp else "f32",
@@ -923,7 +940,7 @@ def main():
                                    "sample": "%d full CFR+ iterations (same tree, same BR cadence) by oracle/cfr_oracle.c "
                                              "with OpenMP; the reference's own Python path is ~400x slower per node "
                                              "(BASELINE.md: 0.448 s/iter on the 1 096-node tree)" % n}
-    print(json.dumps(out))
+    emit((out))
     if world > 1:
         dist.destroy_process_group()
 

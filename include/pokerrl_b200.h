@@ -288,8 +288,13 @@ typedef struct {
     float* avg;
 } prl_trunk_t;
 
+/* peers != NULL fuses the ONE collective of the path into this launch: peers = DEVICE array of n_peers pointers to every rank's
+ * w_total buffer in peer-mapped (symmetric) memory, read over NVLink at element offset peer_offset and summed in rank order
+ * into w_scratch (DEVICE int64[4][n_range]); the caller orders this launch after all ranks' sweeps with a cross-rank barrier.
+ * peers == NULL: g->w_total already holds the global sums (single GPU, or all-reduced by the caller). */
 int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, int eval, int p, int n_sym, const int16_t* sym_perm, int iter,
-                    int delay, float* out_expl, prl_stream_t stream);
+                    int delay, float* out_expl, const int64_t* const* peers, int n_peers, int64_t peer_offset, int64_t* w_scratch,
+                    prl_stream_t stream);
 
 /* Strength-ordered rows <-> natural-order rows.  row_src / row_dst = DEVICE int64[rows_per_board][2] {row on board 0,
  * stride per board} in the strength-ordered table and in a natural-order table of stride ld. */

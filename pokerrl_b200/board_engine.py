@@ -162,7 +162,27 @@ class BoardCFRSolver:
         g.tables, g.board_prob, g.board_mult = self.t_blob.data_ptr(), self.t_prob.data_ptr(), self.t_mult.data_ptr()
         g.regret, g.avg = self.regret.data_ptr(), self.avg.data_ptr()
         self.w_private = torch.zeros((g.grid, 2, self.R), dtype=torch.int64, device=dev)
-        self.w_total = torch.zeros((4, self.R), dtype=torch.int64, device=dev)
+        # chance sums: two generations of [4][R] int64 (a sweep writes one generation while slow peers may still read the other)
+        self._symm = None
+        self.collective = "none" if self.world == 1 else "nccl all_reduce(int64)"
+        if (self.world > 1 and self._reduce_fn is None and os.environ.get("PRL_COLLECTIVE", "p2p") == "p2p"
+                and os.environ.get("PRL_TRUNK", "fused") != "levels"):
+            try:  # symmetric (peer-mapped) memory: the trunk kernel reads every rank's sums over NVLink itself
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                self.w_gens = symm_mem.empty((2, 4, self.R), dtype=torch.int64, device=dev)
+                self.w_gens.zero_()
+                self._symm = symm_mem.rendezvous(self.w_gens, group=self.group if self.group is not None else dist.group.WORLD)
+                self._peer_ptrs = torch.tensor([int(x) for x in self._symm.buffer_ptrs], dtype=torch.int64, device=dev)
+                self.collective = "one-shot NVLink sum inside trunk_kernel (symmetric memory, %d peers)" % self.world
+            except Exception as e:  # noqa: BLE001 - any failure of the peer mapping leaves the NCCL path
+                self._symm = None
+                self.collective = "nccl all_reduce(int64) (symmetric memory unavailable: %s)" % type(e).__name__
+        if self._symm is None:
+            self.w_gens = torch.zeros((2, 4, self.R), dtype=torch.int64, device=dev)
+        self._gen = 0
+        self.w_total = self.w_gens[0]
+        self.w_scratch = torch.zeros((4, self.R), dtype=torch.int64, device=dev)
         g.w_private, g.w_total = self.w_private.data_ptr(), self.w_total.data_ptr()
         self.g = g
         # the trunk in one launch (prl_board_trunk); PRL_TRUNK=levels keeps the level-kernel chain (A/B, cross-check)
@@ -193,11 +213,26 @@ class BoardCFRSolver:
         return t
 
     def _trunk(self, bufs, modes, evaluate, p):
+        peers, n_peers, off = None, 0, 0
+        if self._symm is not None:
+            peers, n_peers, off = C.c_void_p(self._peer_ptrs.data_ptr()), self.world, self._gen * 4 * self.R
         nat.call("prl_board_trunk", C.byref(self.g), C.byref(self._trunk_desc(bufs, modes)), int(evaluate), p, self.n_sym,
                  C.c_void_p(self.t_sym.data_ptr()) if self.n_sym else None, self.iter_counter, self.delay,
-                 C.c_void_p(self._expl.data_ptr()), _stream(self.device))
+                 C.c_void_p(self._expl.data_ptr()), peers, n_peers, off, C.c_void_p(self.w_scratch.data_ptr()),
+                 _stream(self.device))
+
+    def _next_generation(self):
+        """the next sweep(s) write the other generation of the chance sums"""
+        self._gen ^= 1
+        self.w_total = self.w_gens[self._gen]
+        self.g.w_total = self.w_total.data_ptr()
 
     def _reduce(self, view):
+        if self._symm is not None:
+            # all ranks' sweeps are complete and visible before any trunk kernel reads the peers; the trunk kernel sums
+            self._symm.barrier(channel=0)
+            self.n_allreduce += 1
+            return
         if self._reduce_fn is not None:
             self._reduce_fn(view)
         elif self.world > 1:  # the ONE collective of the path; int64 sums are exact in any order
@@ -251,6 +286,7 @@ class BoardCFRSolver:
             self._reduce(self.w_total[:1])
             self._trunk(self.bufs, self.modes, False, p)
             self.modes[p] = nat.STRAT_F32
+            self._next_generation()
             return
         self._sweep_end(self.bufs, p, False)
         self._levels(self.bufs, 1 << p, False, self.algo, p, self.modes, cl, cl, 2)
@@ -283,6 +319,7 @@ class BoardCFRSolver:
                 self._sweep_begin(bufs, p, True, src, src)
             self._reduce(self.w_total)
             self._trunk(bufs, modes, True, -1)
+            self._next_generation()
             e = self._expl.cpu().numpy()
             return sum(float(e[p]) * self.ev_normalizer for p in range(2)) / 2
         self._levels(bufs, 3, True, -1, -1, modes, cl, cl, 1)

@@ -698,8 +698,13 @@ __device__ __forceinline__ float trunk_sigma(const prl_trunk_t& t, int src, int 
     return tab[(size_t)slot * t.ld + h];
 }
 
+// peers != NULL: the cross-GPU sum is done HERE - every rank's fixed-point vector sits in symmetric (peer-mapped) memory and
+// is read over NVLink with coalesced 8-byte loads, rank 0 .. n_peers-1 in order (integers: any order gives the same bits),
+// into w_scratch; the caller has placed a cross-rank barrier between the sweep kernels and this launch.
 template <bool EVAL>
 __global__ void __launch_bounds__(kTrunkThreads) trunk_kernel(const prl_trunk_t t, const long long* __restrict__ w_total,
+                                                              const long long* const* __restrict__ peers, int n_peers,
+                                                              long long peer_offset, long long* __restrict__ w_scratch,
                                                               const int16_t* __restrict__ sym_perm, int n_sym, double inv_scale,
                                                               int p_upd, int iter, int delay, float m_old, float m_new, float* out_expl) {
     __shared__ float ro[kRange + 2];
@@ -709,6 +714,15 @@ __global__ void __launch_bounds__(kTrunkThreads) trunk_kernel(const prl_trunk_t 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t N = (size_t)t.n_buf_nodes, ld = (size_t)t.ld;
     const int seat_lo = EVAL ? 0 : p_upd, seat_hi = EVAL ? 1 : p_upd;
+    if (peers != nullptr) {
+        for (int i = tid; i < (EVAL ? 4 : 1) * kRange; i += kTrunkThreads) {
+            long long s = 0;
+            for (int r = 0; r < n_peers; ++r) s += peers[r][peer_offset + i];
+            w_scratch[i] = s;
+        }
+        __syncthreads();
+        w_total = w_scratch;
+    }
     // 1. the chance node's rows
     for (int p = seat_lo; p <= seat_hi; ++p)
         for (int k = 0; k < (EVAL ? 2 : 1); ++k) {
@@ -970,7 +984,8 @@ extern "C" int prl_board_permute(const prl_board_game_t* g, int rows_per_board, 
 
 // Trunk of seat p's half-iteration (eval == 0) or of an evaluation of both seats (eval != 0) in one launch; see prl_trunk_t.
 extern "C" int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, int eval, int p, int n_sym, const int16_t* sym_perm,
-                               int iter, int delay, float* out_expl, prl_stream_t stream) {
+                               int iter, int delay, float* out_expl, const int64_t* const* peers, int n_peers,
+                               int64_t peer_offset, int64_t* w_scratch, prl_stream_t stream) {
     if (!g || !t || t->n_nodes < 1 || t->n_nodes > 8) return prl::fail("prl_board_trunk: 1..8 trunk nodes");
     if (t->n_range != kRange || g->n_deck != kDeck) return prl::fail("prl_board_trunk: 52-card deck / 1326 hands only");
     if (eval && !out_expl) return prl::fail("prl_board_trunk: out_expl missing");
@@ -982,8 +997,15 @@ extern "C" int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, 
     const float m_old = (iter > delay) ? (float)(cw / (cw + nw)) : 0.0f, m_new = (iter > delay) ? (float)(nw / (cw + nw)) : 1.0f;
     const double inv_scale = 1.0 / (double)(1ull << g->frac_bits);
     const long long* w = reinterpret_cast<const long long*>(g->w_total);
-    if (eval) trunk_kernel<true><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, sym_perm, n_sym, inv_scale, -1, iter, delay, m_old, m_new, out_expl);
-    else trunk_kernel<false><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, sym_perm, n_sym, inv_scale, p, iter, delay, m_old, m_new, out_expl);
+    if (peers && (n_peers < 1 || !w_scratch)) return prl::fail("prl_board_trunk: peer sum needs n_peers >= 1 and w_scratch");
+    const long long* const* pp = reinterpret_cast<const long long* const*>(peers);
+    long long* ws = reinterpret_cast<long long*>(w_scratch);
+    if (eval)
+        trunk_kernel<true><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, pp, n_peers, (long long)peer_offset, ws, sym_perm, n_sym,
+                                                                       inv_scale, -1, iter, delay, m_old, m_new, out_expl);
+    else
+        trunk_kernel<false><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, pp, n_peers, (long long)peer_offset, ws, sym_perm, n_sym,
+                                                                        inv_scale, p, iter, delay, m_old, m_new, out_expl);
     prl::count_launch();
     return prl::check(cudaGetLastError(), "prl_board_trunk");
 }
