@@ -26,8 +26,10 @@ extern "C" {
 typedef void* prl_stream_t; /* cudaStream_t */
 
 /* bumped whenever a struct below changes; prl_abi_version() returns the value the library was built with
-   (2: prl_tree_t gained board_hand_rec / node_rec2 / work_rec2 / level_nfold; 3: board engine, legacy LUT natives) */
-#define PRL_ABI_VERSION 3
+   (2: prl_tree_t gained board_hand_rec / node_rec2 / work_rec2 / level_nfold; 3: board engine, legacy LUT natives;
+    4: prl_tree_t gained the all-in terminals of two-card games: level_nallin / allin_nodes / allin_pot / allin_tiles /
+    allin_partial) */
+#define PRL_ABI_VERSION 4
 
 /* node kinds (game/_/tree/_/nodes.py:8-62 + ValueFiller.py:34-62) */
 enum {
@@ -112,6 +114,15 @@ typedef struct {
                                     terminal entries: {node, board id, pot as float bits, kind | (acted_last & 0xff) << 8} */
     const int64_t* level_nfold;  /* HOST int64[n_levels] or NULL: fold terminals per level (they come first among the
                                     terminals in `order`); lets fold and showdown rows be launched as separate kernels */
+    /* two-card games, all-in showdowns before the board is complete (PRL_KIND_SHOWDOWN_ALLIN; the one-card analogue is
+       ValueFiller.py:160-175): they come LAST among the terminals of a level in `order`; their values are the dense product
+       of the public state's equity matrix with the opponent's reach row (prl_allin_values, tensor cores).  Only all-in
+       nodes that see the ROOT's board are supported (one matrix). */
+    const int64_t* level_nallin; /* HOST int64[n_levels] or NULL (= no such terminals) */
+    const int32_t* allin_nodes;  /* HOST int32[sum of level_nallin]: their node ids, ascending (= by level) */
+    const float* allin_pot;      /* HOST float[same]: pot of each */
+    const void* allin_tiles;     /* DEVICE: equity matrix as bf16 operand tiles (prl_allin_equity_finish) */
+    float* allin_partial;        /* DEVICE scratch, prl_allin_partial_bytes(n_range) bytes */
 } prl_tree_t;
 
 /* Caller-owned work buffers. */
@@ -305,6 +316,31 @@ int prl_board_permute(const prl_board_game_t* g, int rows_per_board, const int64
  * 7-card Hold'em hand evaluation (replaces lib_hand_eval.so; int32 strength, higher = better, identical encoding incl.
  * the quads-kicker quirk - see oracle/hand_eval_oracle.c).  Cards are 1D ids c = rank*4 + suit.
  * ------------------------------------------------------------------------------------------------------------------ */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * All-in showdowns before the board is complete, two-card games (csrc/allin_dense.cu).  The reference enumerates the
+ * missing board cards per terminal (ValueFiller.py:160-175 `_get_call_eq_preflop`, one-card games only); here the public
+ * state's EQUITY MATRIX  E[h][h'] = sum over the sym_perm permutations q and the completions b of the board of
+ * w_b * sign(rank_b(q(h)) - rank_b(h')) (0 where a hand is blocked or the two hands share a card) is built once, stored
+ * as three bf16 split planes in tcgen05 operand tiles, and every all-in terminal costs one column of a tensor-core GEMM
+ * (BASELINE.json north_star: "tensor cores used only for the dense 1326x1326 Hold'em showdown equity contraction").
+ *   prl_allin_equity_accumulate: ec (DEVICE double[n_range][n_range], zeroed by the caller) += sum_b weight[b] * S_b for a chunk
+ *     of boards; ranks DEVICE int32[n_boards][n_range] (prl_hand_rank_boards), weight DEVICE double[n_boards] (deal probability
+ *     x weight in the parent's sum).
+ *   prl_allin_equity_finish: symmetrises over sym_perm (NULL / n_sym <= 1: none), masks hands sharing a card, splits into
+ *     three bf16 planes (24 mantissa bits) and writes the operand tiles (prl_allin_tiles_bytes bytes).
+ *   prl_allin_values: for column c < n_cols: y_rows[c][h] (and y2_rows[c][h] if y2_rows and y2_rows[c]) =
+ *     scale[c] * sum_h' E[h][h'] * x_rows[c][h'].  x_rows / y_rows / y2_rows / scale are HOST arrays (of DEVICE row pointers);
+ *     fp32 operands are split into three bf16 planes on the fly, products accumulate in fp32 in tensor memory.
+ */
+int64_t prl_allin_tiles_bytes(int n_range);
+int64_t prl_allin_partial_bytes(int n_range);
+int prl_allin_equity_accumulate(const int32_t* ranks, const double* weight, int n_boards, int n_range, double* ec,
+                                prl_stream_t stream);
+int prl_allin_equity_finish(const double* ec, int n_range, const int8_t* hand_cards, const int16_t* sym_perm, int n_sym,
+                            void* tiles, prl_stream_t stream);
+int prl_allin_values(const void* tiles, int n_range, const float* const* x_rows, float* const* y_rows, float* const* y2_rows,
+                     const float* scale, int n_cols, float* partial, prl_stream_t stream);
 
 /* HoldemRules.get_hand_rank_all_hands_on_given_boards (game_rules.py:213-217) on device buffers:
  * boards = DEVICE int8[n_boards][5], out = DEVICE int32[n_boards][1326] (-1 where the hand is blocked by the board;

@@ -35,6 +35,23 @@ def sign_matrix(ranks, compat, blocked):
     return s * (compat & ~blocked[:, None] & ~blocked[None, :])
 
 
+def allin_equity_matrix(ranks, weight, hand_cards, n_deck, sym_perm=None):
+    """E[h][h'] = sum over the hand permutations q and the boards b of weight_b * S_b[q(h)][h'] with S_b = sign_matrix of
+    board b (float64, brute force): the value rows of an all-in showdown before the deal are K * pot / 2 * E @ reach_opp -
+    exactly what a chance node over those boards with showdown children and board_prob * board_mult = weight would give."""
+    R = ranks.shape[1]
+    inc = np.zeros((R, n_deck))
+    for k in range(hand_cards.shape[1]):
+        inc[np.arange(R), hand_cards[:, k]] = 1
+    compat = (inc @ inc.T) == 0
+    ec = np.zeros((R, R))
+    for b in range(ranks.shape[0]):
+        ec += weight[b] * sign_matrix(ranks[b], compat, ranks[b] < 0)
+    if sym_perm is None:
+        return ec
+    return sum(ec[np.asarray(pm, np.int64)] for pm in sym_perm)
+
+
 class Oracle2Tree:
     def __init__(self, ft, hand_cards, board_ranks, board_prob, board_mult, sym_perm=None, eq_const=None):
         """ft: FlatTree; hand_cards int[R, n_hole]; board_ranks int32[n_boards_total, R] (global board id order,
@@ -70,6 +87,7 @@ class Oracle2Tree:
         self.ev_br = np.zeros((self.N, 2, R))
         self.strategy = [None] * self.N
         self._sign = {}
+        self.allin_equity = None  # float64 [R, R], see allin_equity_matrix()
 
     def decision_nodes(self):
         ft = self.ft
@@ -121,8 +139,11 @@ class Oracle2Tree:
                         eq[p] = -e if ft.acted_last[n] == p else e
                     elif k == KIND_SHOWDOWN:
                         eq[p] = self._sign_matrix(b) @ ro
-                    else:
-                        raise NotImplementedError("all-in showdown before the board is complete (two-card games)")
+                    else:  # all-in before the deal: the showdown rows of every board it runs out over, summed like a
+                        # chance node's children would be (ValueFiller.py:160-175 is the one-card analogue)
+                        if self.allin_equity is None:
+                            raise NotImplementedError("all-in showdown before the board is complete: set allin_equity")
+                        eq[p] = self.allin_equity @ ro
                 eq *= self.K
                 if b >= 0:
                     eq[:, self.board_blocked[b]] = 0.0

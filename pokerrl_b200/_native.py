@@ -7,12 +7,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpokerrl_b200.so")
+# PRL_LIB_PATH: another build of the same library (tools/build_variants.py writes kernel-variant builds for A/B timing)
+LIB_PATH = os.environ.get("PRL_LIB_PATH") or os.path.join(_HERE, "lib", "libpokerrl_b200.so")
 
 # enums of include/pokerrl_b200.h
 KIND_P0, KIND_P1, KIND_CHANCE, KIND_FOLD, KIND_SHOWDOWN, KIND_SHOWDOWN_ALLIN = range(6)
 ALGO_VANILLA, ALGO_CFR_PLUS, ALGO_LINEAR = 0, 1, 2
-ABI_VERSION = 3  # include/pokerrl_b200.h: PRL_ABI_VERSION
+ABI_VERSION = 4  # include/pokerrl_b200.h: PRL_ABI_VERSION
 STRAT_F32, STRAT_UNIFORM64, STRAT_AVG_F64, STRAT_AVG_SUM, STRAT_AVG_F32 = range(5)
 
 
@@ -31,6 +32,8 @@ class PrlTree(C.Structure):
         ("board_row_order", C.c_void_p), ("board_row_pos", C.c_void_p), ("board_complete", C.c_void_p),
         ("n_sym", C.c_int32), ("sym_perm", C.c_void_p), ("eq_const", C.c_float), ("board_hand_rec", C.c_void_p),
         ("node_rec2", C.c_void_p), ("work_rec2", C.c_void_p), ("level_nfold", C.c_void_p),
+        ("level_nallin", C.c_void_p), ("allin_nodes", C.c_void_p), ("allin_pot", C.c_void_p), ("allin_tiles", C.c_void_p),
+        ("allin_partial", C.c_void_p),
     ]
 
 
@@ -123,6 +126,14 @@ def lib():
     L.prl_lbr_checkdown_equity.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
     L.prl_lbr_checkdown_equity.restype = C.c_int
+    L.prl_allin_tiles_bytes.argtypes = L.prl_allin_partial_bytes.argtypes = [C.c_int]
+    L.prl_allin_tiles_bytes.restype = L.prl_allin_partial_bytes.restype = C.c_int64
+    L.prl_allin_equity_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.prl_allin_equity_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.prl_allin_values.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p]
+    for f in ("prl_allin_equity_accumulate", "prl_allin_equity_finish", "prl_allin_values"):
+        getattr(L, f).restype = C.c_int
     gp = C.POINTER(PrlBoardGame)
     L.prl_board_layout.argtypes = [C.POINTER(C.c_int32)]
     L.prl_board_grid.argtypes = []

@@ -25,6 +25,7 @@ SOURCES = {
     "cfr_board.cu": ["--expt-relaxed-constexpr"],
     "env_kernels.cu": [],
     "lbr_rollout.cu": [],
+    "allin_dense.cu": [],
 }
 
 

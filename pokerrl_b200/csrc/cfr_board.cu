@@ -48,6 +48,21 @@ constexpr int kBlobA = kRecBytes + kShBytes;                // 10 880 B, needed 
 constexpr int kBlobBytes = kBlobA + kRowIdxBytes;           // 15 392 B
 static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
+// kernel variants (A/B switches; the defaults are the measured winners, profiles/r02_q_sweep_variants.md)
+#ifndef PRL_BV_RED
+#define PRL_BV_RED 1         // chance sums by 64-bit RED instead of load + add + store
+#endif
+#ifndef PRL_BV_P1PIPE
+#define PRL_BV_P1PIPE 1      // P1 rows: only the first position is requested one unit ahead, the others pipelined inside P1
+#endif
+#ifndef PRL_BV_FOLDLIN
+#define PRL_BV_FOLDLIN 1     // update form: card-row sums of the fold vectors from the showdown vectors' row totals (linearity)
+#endif
+#ifndef PRL_BV_SERIALSCAN
+#define PRL_BV_SERIALSCAN 0  // main prefix sums: one warp per vector, 35 consecutive positions per lane, no cross-warp stage
+#endif                       // (measured: +1 % alone, -5 % on top of the other three - seven idle warps cost more than the shuffles)
+constexpr bool kVRed = PRL_BV_RED, kVP1Pipe = PRL_BV_P1PIPE, kVFoldLin = PRL_BV_FOLDLIN, kVSerialScan = PRL_BV_SERIALSCAN;
+
 constexpr int kThreads = 384;  // 12 warps; 3 strength positions per thread (3 * 384 = 1152 >= 1081: 94 % of the lanes busy)
 constexpr int kPerThread = 3;
 constexpr int kWarps = kThreads / 32;
@@ -87,6 +102,16 @@ struct ShapeFHP {
     }
 };
 static_assert(ShapeFHP::count(4) == ShapeFHP::n_sd && ShapeFHP::count(3) == ShapeFHP::n_fold, "shape");
+// Reach of the OPPONENT of seat P at fold terminal f as a combination of its reach at the showdown terminals (strategies sum
+// to one, own nodes copy the reach): x_fold[f] = sum_v coef(P, f, v) * x_sd[v].  Every linear functional of the fold vectors
+// (their card-row sums) follows from the showdown vectors' at no cost.  tools/fold_relations.py derives the table.
+struct FoldLinFHP {
+    static constexpr int coef(int P, int f, int v) {
+        constexpr int c[2][4][5] = {{{0, 1, 0, 0, 0}, {1, 0, -1, 0, -1}, {0, 1, 0, -1, 0}, {0, 0, 0, 0, 1}},
+                                    {{1, -1, 1, -1, 0}, {0, 0, 1, 0, 0}, {0, 0, 0, 1, 0}, {0, 0, 1, 0, -1}}};
+        return c[P][f][v];
+    }
+};
 static_assert(ShapeFHP::rows_of_seat(0) + ShapeFHP::rows_of_seat(1) == ShapeFHP::rows, "shape");
 
 template <int I, int N, class F>
@@ -116,9 +141,11 @@ constexpr int kCsOff = kRowIdxOff + kRowIdxBytes;                           // f
 constexpr int kCsdOff = kCsOff + ShapeFHP::n_fold * kRowPad * 4;            // double csd[4][48]: the same sums before rounding
 constexpr int kMiscOff = kCsdOff + ShapeFHP::n_fold * kRowPad * 8;          // double wsum[5][16], wexc[5][16]; float tf[8]
 constexpr int kMiscBytes = (5 * 16 + 5 * 16) * 8 + 8 * 4;
-constexpr int kBarOff = kMiscOff + kMiscBytes;                              // 3 mbarriers
+constexpr int kRowTotOff = kMiscOff + kMiscBytes;                           // double rowtot[5][48]: card-row totals of the showdown vectors
+constexpr int kRowTotBytes = ShapeFHP::n_sd * kRowPad * 8;
+constexpr int kBarOff = kRowTotOff + kRowTotBytes;                          // 3 mbarriers
 constexpr int kSmemBytes = kBarOff + 32;
-static_assert(kBlobOff % 16 == 0 && kRowIdxOff % 16 == 0 && kCsdOff % 8 == 0 && kMiscOff % 8 == 0 && kBarOff % 8 == 0, "alignment");
+static_assert(kBlobOff % 16 == 0 && kRowIdxOff % 16 == 0 && kCsdOff % 8 == 0 && kMiscOff % 8 == 0 && kRowTotOff % 8 == 0 && kBarOff % 8 == 0, "alignment");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 
 struct SweepArgs {
@@ -207,6 +234,8 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     float* tf = reinterpret_cast<float*>(wexc + 5 * 16);         // [8]     totals of the fold vectors
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);  // [0], [1]: blob A buffers; [2]: card rows
     const int16_t* rowidx = reinterpret_cast<const int16_t*>(smem + kRowIdxOff);
+    double* rowtot = reinterpret_cast<double*>(smem + kRowTotOff);  // [5][48]
+    constexpr bool kLin = kVFoldLin && !EVAL;  // evaluation may read average-strategy rows, which sum to one only up to rounding
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const prl_board_game_t& G = a.g;
@@ -252,19 +281,23 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         prefetch_rows(j);
     }
 
-    // P1 inputs of the thread's three strength positions (opponent rows + trunk reach), requested one unit ahead
-    float p1_g[kPerThread][NOPP], p1_x0[kPerThread];
-    auto p1_load = [&](int jj, const int16_t* sh_jj) {
-        const float* rows = tab_opp + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb + tid;
+    // P1 inputs of the thread's three strength positions (opponent rows + trunk reach).  kVP1Pipe: only the first position
+    // is requested one unit ahead (8 registers live across the unit's last barrier - 24 spilled to local memory and made the
+    // warp wait for the loads there); the other two are requested inside P1, one position ahead of their use.
+    constexpr int kP1Ahead = kVP1Pipe ? 1 : kPerThread;
+    float p1_g[kP1Ahead][NOPP], p1_x0[kP1Ahead];
+    auto p1_load_k = [&](int jj, const int16_t* sh_jj, int k, float (&g)[NOPP], float& x0) {
+        const int i = tid + k * kThreads;
+        if (i < kLive) {
+            const float* rows = tab_opp + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb + i;
 #pragma unroll
-        for (int k = 0; k < kPerThread; ++k) {
-            const int i = tid + k * kThreads;
-            if (i < kLive) {
-#pragma unroll
-                for (int r = 0; r < NOPP; ++r) p1_g[k][r] = ld_stream(rows + (size_t)r * kLdb + k * kThreads);
-                p1_x0[k] = __ldg(a.trunk_reach_opp + sh_jj[i]);
-            }
+            for (int r = 0; r < NOPP; ++r) g[r] = ld_stream(rows + (size_t)r * kLdb);
+            x0 = __ldg(a.trunk_reach_opp + sh_jj[i]);
         }
+    };
+    auto p1_load = [&](int jj, const int16_t* sh_jj) {
+#pragma unroll
+        for (int k = 0; k < kP1Ahead; ++k) p1_load_k(jj, sh_jj, k, p1_g[k], p1_x0[k]);
     };
 
     for (int it = 0; j < nb; j += gridDim.x, ++it) {
@@ -287,37 +320,45 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // ------------------------------------------------------------------------------------------ P1: reach, top-down
         // x[i] = reach of the OPPONENT at local node i (StrategyFiller.py:118-146); terminal rows go to S in strength order.
         // The rows were requested before the previous unit's last barrier (p1_load): their latency is off this path.
-        {
+        auto p1_hand = [&](int k, const float (&gk)[NOPP], float x0k) {
+            const int i = tid + k * kThreads;
+            if (i < kLive) {
+                float x[SH::N];
+                x[0] = x0k * prob;  // the deal (StrategyFiller.py:137-140); blocked hands are not stored at all
+                static_for<0, SH::N>([&](auto I) {
+                    constexpr int n = decltype(I)::value;
+                    constexpr int A = SH::n_children(n);
+                    if constexpr (SH::kind(n) <= 1) {
+                        constexpr int fc = SH::first_child(n);
+                        if constexpr (SH::kind(n) == OPP) {
+                            float gg[A], s[A];
 #pragma unroll
-            for (int k = 0; k < kPerThread; ++k) {
-                const int i = tid + k * kThreads;
-                if (i < kLive) {
-                    float x[SH::N];
-                    x[0] = p1_x0[k] * prob;  // the deal (StrategyFiller.py:137-140); blocked hands are not stored at all
-                    static_for<0, SH::N>([&](auto I) {
-                        constexpr int n = decltype(I)::value;
-                        constexpr int A = SH::n_children(n);
-                        if constexpr (SH::kind(n) <= 1) {
-                            constexpr int fc = SH::first_child(n);
-                            if constexpr (SH::kind(n) == OPP) {
-                                float gg[A], s[A];
+                            for (int c = 0; c < A; ++c) gg[c] = gk[SH::row_of(fc + c) - OPP0];
+                            node_strategy<A>(gg, EVAL ? a.src_opp : 0, s);
 #pragma unroll
-                                for (int c = 0; c < A; ++c) gg[c] = p1_g[k][SH::row_of(fc + c) - OPP0];
-                                node_strategy<A>(gg, EVAL ? a.src_opp : 0, s);
-#pragma unroll
-                                for (int c = 0; c < A; ++c) x[fc + c] = x[n] * s[c];
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < A; ++c) x[fc + c] = x[n];
-                            }
-                        } else if constexpr (SH::kind(n) == 4) {
-                            S[SH::vec_index(n) * kLdb + i] = x[n];
+                            for (int c = 0; c < A; ++c) x[fc + c] = x[n] * s[c];
                         } else {
-                            S[(NSD + SH::vec_index(n)) * kLdb + i] = x[n];
+#pragma unroll
+                            for (int c = 0; c < A; ++c) x[fc + c] = x[n];
                         }
-                    });
-                }
+                    } else if constexpr (SH::kind(n) == 4) {
+                        S[SH::vec_index(n) * kLdb + i] = x[n];
+                    } else {
+                        S[(NSD + SH::vec_index(n)) * kLdb + i] = x[n];
+                    }
+                });
             }
+        };
+        if constexpr (kVP1Pipe) {
+            float gB[NOPP], gC[NOPP], xB = 0.0f, xC = 0.0f;
+            p1_load_k(j, sh, 1, gB, xB);
+            p1_hand(0, p1_g[0], p1_x0[0]);
+            p1_load_k(j, sh, 2, gC, xC);
+            p1_hand(1, gB, xB);
+            p1_hand(2, gC, xC);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) p1_hand(k, p1_g[k], p1_x0[k]);
         }
         __syncthreads();  // B1: S complete
 
@@ -327,8 +368,9 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // fold vectors: the row's mass cs[f][lc].  Two groups of 47 quads share the nine vectors (SD 0-2 + fold 0-1 | SD 3-4 +
         // fold 2-3); the other threads start on the main scans, which only read S as well.
         mbar_wait(&bars[2], it & 1);
-        float a0[NSD], a1[NSD], a2[NSD];
-        double pre[NSD];
+        constexpr int NLEG = kVSerialScan ? 1 : NSD;  // state of the thread-per-three-positions scan (legacy variant)
+        float a0[NLEG], a1[NLEG], a2[NLEG];
+        double pre[NLEG];
         constexpr int kQuadThreads = kLiveCards * 4;  // 188
         if (warp < (2 * kQuadThreads + 31) / 32) {   // whole warps (the quad shuffles name every lane)
             const int grp = (tid >= kQuadThreads) ? 1 : 0;
@@ -348,10 +390,18 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 const float* Sv = S + v * kLdb;
                 float inc[kRowSeg];
                 float run = 0.0f;
+                double drun = 0.0;  // kLin: the row's total in double (the fold vectors' row sums derive from these)
 #pragma unroll
                 for (int e = 0; e < kRowSeg; ++e) {
+                    const float xv = Sv[idx[e]];
                     inc[e] = run;
-                    run += Sv[idx[e]];
+                    run += xv;
+                    if constexpr (kLin) drun += (double)xv;
+                }
+                if constexpr (kLin) {
+                    drun += __shfl_xor_sync(qmask, drun, 1, 4);
+                    drun += __shfl_xor_sync(qmask, drun, 2, 4);
+                    if (row_live && q == 0) rowtot[v * kRowPad + lc] = drun;
                 }
                 float sc = run;  // inclusive scan over the quad
                 float tt = __shfl_up_sync(qmask, sc, 1, 4);
@@ -366,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                     if (row_live && q * kRowSeg + e < kErStride) row[e] = off + inc[e];
             }
 #pragma unroll 1
-            for (int f = 2 * grp; f < 2 * grp + 2; ++f) {
+            for (int f = 2 * grp; f < (kLin ? 0 : 2 * grp + 2); ++f) {  // kLin: nothing to gather for the fold vectors
                 const float* Sv = S + (NSD + f) * kLdb;
                 double run = 0.0;  // double: the fold value subtracts these sums from the total (cancellation)
 #pragma unroll
@@ -379,11 +429,39 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         __syncwarp();
         // ------------------------------------------------------------------------------------------ P2b: main scans, part 1
         // centred exclusive prefix sums over the strength order: E[k] = (mass of the k weakest hands) - total / 2, k = 0 ..
-        // 1081.  Thread t owns positions 3t .. 3t+2; sums in double (the showdown value is a difference of two prefixes).
-        {
+        // 1081, sums in double (the showdown value is a difference of two prefixes).
+        // kVSerialScan: ONE warp per vector (warps 7..11, the lighter card-row group), lane l owns the 35 consecutive positions
+        // 35 l .. 35 l + 34 (odd stride: conflict-free): a serial pass for the lane totals, one warp scan, and after B2 a second
+        // serial pass that writes the prefixes in place - a third of the instructions of the three-positions-per-thread scan,
+        // no cross-warp stage (its single-warp section made eleven warps wait at a barrier of its own).
+        constexpr int kScanWarp0 = 7, kScanChunk = 35;
+        static_assert(kScanWarp0 + NSD <= kWarps && 32 * kScanChunk > kLive + 1 && (kScanChunk & 1), "scan geometry");
+        const bool scan_warp = kVSerialScan && warp >= kScanWarp0 && warp < kScanWarp0 + NSD;
+        double scan_base = 0.0;
+        if constexpr (kVSerialScan) {
+            if (scan_warp) {
+                const float* Sv = S + (warp - kScanWarp0) * kLdb;
+                const int p0 = lane * kScanChunk;
+                double tot = 0.0;
+#pragma unroll 7
+                for (int e = 0; e < kScanChunk; ++e) {
+                    const int p = p0 + e;
+                    const float xv = (p < kLive) ? Sv[p] : 0.0f;
+                    tot += (double)xv;
+                }
+                double incw = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double tt = __shfl_up_sync(0xffffffffu, incw, o);
+                    if (lane >= o) incw += tt;
+                }
+                const double total = __shfl_sync(0xffffffffu, incw, 31);
+                scan_base = (incw - tot) - 0.5 * total;
+            }
+        } else {
             const int b0 = 3 * tid;
 #pragma unroll
-            for (int v = 0; v < NSD; ++v) {
+            for (int v = 0; v < NLEG; ++v) {
                 const float* Sv = S + v * kLdb;
                 a0[v] = (b0 < kLive) ? Sv[b0] : 0.0f;
                 a1[v] = (b0 + 1 < kLive) ? Sv[b0 + 1] : 0.0f;
@@ -424,37 +502,74 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             mbar_expect_tx(&bars[2], kRowIdxBytes);
             bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)jn * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
         }
-        if (warp == 0) {
+        // card-row sums cs[f][card] and total tf[f] of fold vector f (total = half the sum of its card rows): from the gathered
+        // sums csd, or - kLin - as the combination FoldLinFHP of the showdown vectors' row totals
+        auto fold_finish = [&](auto F) {
+            constexpr int f = decltype(F)::value;
+            double c0 = 0.0, c1 = 0.0;
+            if constexpr (kLin) {
+                static_assert(std::is_same<SH, ShapeFHP>::value, "FoldLinFHP belongs to ShapeFHP");
+                static_for<0, NSD>([&](auto V) {
+                    constexpr int v = decltype(V)::value;
+                    constexpr int cf = FoldLinFHP::coef(P, f, v);
+                    if constexpr (cf != 0) {
+                        const double r0 = (lane < kLiveCards) ? rowtot[v * kRowPad + lane] : 0.0;
+                        const double r1 = (lane + 32 < kLiveCards) ? rowtot[v * kRowPad + lane + 32] : 0.0;
+                        c0 = (cf > 0) ? c0 + r0 : c0 - r0;
+                        c1 = (cf > 0) ? c1 + r1 : c1 - r1;
+                    }
+                });
+            } else {
+                c0 = (lane < kLiveCards) ? csd[f * kRowPad + lane] : 0.0;
+                c1 = (lane + 32 < kLiveCards) ? csd[f * kRowPad + lane + 32] : 0.0;
+            }
+            double s2 = c0 + c1;
 #pragma unroll
-            for (int v = 0; v < NSD; ++v) {  // exclusive scan of the 14 warp totals
-                const double w = (lane < kWarps) ? wsum[v * 16 + lane] : 0.0;
-                double sc = w;
-#pragma unroll
-                for (int o = 1; o < 16; o <<= 1) {
-                    const double tt = __shfl_up_sync(0xffffffffu, sc, o);
-                    if (lane >= o) sc += tt;
+            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (lane == 0) tf[f] = (float)(0.5 * s2);
+            if (lane < kLiveCards) cs[f * kRowPad + lane] = (float)c0;  // float copies for the per-hand epilogue
+            if (lane + 32 < kLiveCards) cs[f * kRowPad + lane + 32] = (float)c1;
+        };
+        if constexpr (kVSerialScan) {
+            if (scan_warp) {  // second serial pass: the prefixes in place
+                float* Sv = S + (warp - kScanWarp0) * kLdb;
+                const int p0 = lane * kScanChunk;
+                double run = scan_base;
+#pragma unroll 7
+                for (int e = 0; e < kScanChunk; ++e) {
+                    const int p = p0 + e;
+                    if (p <= kLive) {
+                        const float xv = (p < kLive) ? Sv[p] : 0.0f;
+                        Sv[p] = (float)run;
+                        run += (double)xv;
+                    }
                 }
-                const double total = __shfl_sync(0xffffffffu, sc, kWarps - 1);
-                if (lane < kWarps) wexc[v * 16 + lane] = (sc - w) - 0.5 * total;
+            } else if (warp < NF) {
+                static_for<0, NF>([&](auto F) {
+                    if (warp == decltype(F)::value) fold_finish(F);
+                });
             }
-        } else if (warp == 1) {
+        } else {
+            if (warp == 0) {
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {  // total of a fold vector = half the sum of its card rows
-                const double c0 = (lane < kLiveCards) ? csd[f * kRowPad + lane] : 0.0;
-                const double c1 = (lane + 32 < kLiveCards) ? csd[f * kRowPad + lane + 32] : 0.0;
-                double s2 = c0 + c1;
+                for (int v = 0; v < NLEG; ++v) {  // exclusive scan of the 12 warp totals
+                    const double w = (lane < kWarps) ? wsum[v * 16 + lane] : 0.0;
+                    double sc = w;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                if (lane == 0) tf[f] = (float)(0.5 * s2);
-                if (lane < kLiveCards) cs[f * kRowPad + lane] = (float)c0;  // float copies for the per-hand epilogue
-                if (lane + 32 < kLiveCards) cs[f * kRowPad + lane + 32] = (float)c1;
+                    for (int o = 1; o < 16; o <<= 1) {
+                        const double tt = __shfl_up_sync(0xffffffffu, sc, o);
+                        if (lane >= o) sc += tt;
+                    }
+                    const double total = __shfl_sync(0xffffffffu, sc, kWarps - 1);
+                    if (lane < kWarps) wexc[v * 16 + lane] = (sc - w) - 0.5 * total;
+                }
+            } else if (warp == 1) {
+                static_for<0, NF>([&](auto F) { fold_finish(F); });
             }
-        }
-        __syncthreads();  // B3
-        {
+            __syncthreads();  // B3
             const int b0 = 3 * tid;
 #pragma unroll
-            for (int v = 0; v < NSD; ++v) {
+            for (int v = 0; v < NLEG; ++v) {
                 float* Sv = S + v * kLdb;
                 double run = pre[v] + wexc[v * 16 + warp];
                 if (b0 <= kLive) Sv[b0] = (float)run;
@@ -472,9 +587,11 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             const uint64_t w = rec[i];
             const int hand = sh[i];
             long long* wacc = wp + hand;
-            const long long w_ev = *wacc;
-            long long w_br = 0;
-            if constexpr (EVAL) w_br = wacc[kRange];
+            long long w_ev = 0, w_br = 0;
+            if constexpr (!kVRed) {
+                w_ev = *wacc;
+                if constexpr (EVAL) w_br = wacc[kRange];
+            }
             const int gs = (int)(w & 0x7ffu), ge = (int)((w >> 11) & 0x7ffu);
             const int lc1 = (int)((w >> 22) & 0x3fu), lc2 = (int)((w >> 28) & 0x3fu);
             const int o1 = lc1 * kErStride + (int)((w >> 34) & 0x3fu), o1e = o1 + (int)((w >> 40) & 0x3fu);
@@ -546,8 +663,14 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 }
             });
             // the board's contribution to its parent's sum (ValueFiller.py:76-78), 64-bit fixed point
-            *wacc = w_ev + __double2ll_rn((double)e[0] * fx);
-            if constexpr (EVAL) wacc[kRange] = w_br + __double2ll_rn((double)br[0] * fx);
+            if constexpr (kVRed) {  // fire-and-forget 64-bit RED into the CTA's private vector: nothing to wait for
+                atomicAdd(reinterpret_cast<unsigned long long*>(wacc), (unsigned long long)__double2ll_rn((double)e[0] * fx));
+                if constexpr (EVAL)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(wacc + kRange), (unsigned long long)__double2ll_rn((double)br[0] * fx));
+            } else {
+                *wacc = w_ev + __double2ll_rn((double)e[0] * fx);
+                if constexpr (EVAL) wacc[kRange] = w_br + __double2ll_rn((double)br[0] * fx);
+            }
         };
         // software pipeline over the thread's three strength positions: the next position's rows are in flight while the
         // current one is evaluated (position 0 was requested before the prefix sums were written back)
@@ -567,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     __syncthreads();
     unsigned long long* wt = reinterpret_cast<unsigned long long*>(G.w_total) + (EVAL ? 2 * P * kRange : 0);  // eval: [seat][ev, ev_br]
     for (int h = tid; h < (EVAL ? 2 : 1) * kRange; h += kThreads) {
-        const long long v = wp[h];
+        const long long v = __ldcg(wp + h);  // L2: where the REDs landed
         if (v != 0) atomicAdd(wt + h, (unsigned long long)v);
     }
 }

@@ -14,6 +14,7 @@
 // instead of the O(R^2) sign-matrix product: these rows are HBM-bound, the dense 1326x1326 contraction (tensor cores)
 // would only add work - see DESIGN.md §6.
 #include <cuda_runtime.h>
+#include <vector>
 #include <stdint.h>
 
 #include "pokerrl_b200.h"
@@ -1118,10 +1119,42 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
     int arr_mask = 0;
     for (int p = 0; p < 2; ++p)
         if (c.mask & (1 << p)) arr_mask |= (1 << (2 * p)) | (with_br ? (2 << (2 * p)) : 0);
+    // all-in showdowns before the deal (last among the terminals of their level): their inputs - the opponent's reach rows -
+    // are complete before the sweep starts, so all of them are evaluated up front by the dense tensor-core product
+    if (T.level_nallin && chance_phase != 2) {
+        std::vector<const float*> xr;
+        std::vector<float*> yr, y2r;
+        std::vector<float> sc;
+        int first = 0;
+        const size_t N = (size_t)T.n_nodes, ld = (size_t)T.ld;
+        for (int d = 0; d < T.n_levels; ++d) {
+            const int na = (int)T.level_nallin[d];
+            if (d >= d_lo && d <= d_hi)
+                for (int k = 0; k < na; ++k) {
+                    const size_t node = (size_t)T.allin_nodes[first + k];
+                    for (int p = 0; p < 2; ++p) {
+                        if (!(c.mask & (1 << p))) continue;
+                        xr.push_back(c.B.reach + ((size_t)(1 - p) * N + node) * ld);
+                        yr.push_back(c.B.ev + ((size_t)p * N + node) * ld);
+                        y2r.push_back(with_br ? c.B.ev_br + ((size_t)p * N + node) * ld : nullptr);
+                        sc.push_back(T.eq_const * T.allin_pot[first + k] * 0.5f);  // ValueFiller.py:160-175 with K, pot / 2
+                    }
+                }
+            first += na;
+        }
+        if (!xr.empty()) {
+            if (!T.allin_tiles || !T.allin_partial || !T.allin_nodes || !T.allin_pot)
+                return prl::fail("prl(two-card): all-in terminals need allin_nodes / allin_pot / allin_tiles / allin_partial");
+            if (int e = prl_allin_values(T.allin_tiles, T.n_range, xr.data(), yr.data(), y2r.data(), sc.data(), (int)xr.size(),
+                                         T.allin_partial, (prl_stream_t)s))
+                return e;
+        }
+    }
     for (int d = d_hi; d >= d_lo; --d) {
         const int lo = (int)T.level_start[d], n_all = (int)(T.level_start[d + 1] - T.level_start[d]);
         const int n_dec = (int)T.level_ndec[d], n_nonterm = (int)T.level_nonterm[d];
-        const int n_chance = n_nonterm - n_dec, n_term = n_all - n_nonterm;
+        const int n_chance = n_nonterm - n_dec;
+        const int n_term = n_all - n_nonterm - (T.level_nallin ? (int)T.level_nallin[d] : 0);  // fold + showdown rows
         if (n_term > 0 && chance_phase != 2) {
             c.lo = lo + n_nonterm;
             c.n = n_term;

@@ -131,13 +131,23 @@ class FlatTree:
         if self.rules.N_HOLE_CARDS == 2:
             from pokerrl_b200.game.holdem_boards import BoardSpec, MultiStreetBoards
             n_cd = max(n.cdepth for n in self.abs_nodes)
-            if any(n.kind == KIND_SHOWDOWN_ALLIN for n in self.abs_nodes):
-                raise NotImplementedError("all-in showdowns before the board is complete in two-card games")
+            allin = [n for n in self.abs_nodes if n.kind == KIND_SHOWDOWN_ALLIN]
+            if allin and (any(n.cdepth != 0 for n in allin) or isinstance(board_spec, MultiStreetBoards) or root_state is not None):
+                raise NotImplementedError("two-card games: all-in showdowns are supported before the first deal of a "
+                                          "single-chance-layer game only (one equity matrix, csrc/allin_dense.cu)")
             if board_spec is None:
                 if n_cd > 1 or root_state is not None:
                     raise ValueError("sub-games / multi-street two-card trees need an explicit MultiStreetBoards spec")
                 board_spec = BoardSpec.full_game(self.rules)
             self.board_spec = board_spec
+            # boards an all-in showdown before the deal runs out over (DeviceTree builds the equity matrix from them)
+            self.allin_spec = board_spec if allin else None
+            if n_cd == 0:  # e.g. a push / fold game: no chance node at all, the board spec only feeds the equity matrix
+                assert isinstance(board_spec, BoardSpec)
+                self.board_prob = np.ones(1, np.float32)
+                self.board_mult = np.ones(1, np.float32)
+                self._expand(([np.zeros((1, 0), np.int8)], [np.zeros(1, np.int32)]))
+                return
             if isinstance(board_spec, MultiStreetBoards):
                 assert board_spec.n_layers == n_cd, (board_spec.n_layers, n_cd)
                 board_tables = (board_spec.boards, board_spec.parents)

@@ -211,11 +211,30 @@ class DeviceTree:
         d.sym_perm = self.t_sym_perm.data_ptr() if sp is not None else None
         n_deck, n_hole = rules.N_CARDS_IN_DECK, rules.N_HOLE_CARDS
         d.eq_const = comb(n_deck, n_hole) / comb(n_deck - n_hole, n_hole)
+        self._init_allin(ft, d, complete)
         # scratch of the chance-node reductions (see prl_buffers_t.workspace)
         max_chance_per_level = max([int((ft.kind[int(ft.level_start[k]):int(ft.level_start[k + 1])] == nat.KIND_CHANCE).sum())
                                     for k in range(ft.n_levels)] + [0])
         chunks = -(-d.max_chance_children // 128)
         self.workspace_bytes = 4 * max(1, max_chance_per_level) * (chunks + 1) * self.ld * 4
+
+    def _init_allin(self, ft, d, complete):
+        """All-in showdowns before the deal (PRL_KIND_SHOWDOWN_ALLIN): the equity matrix of the boards they run out over
+        (ft.allin_spec) as tensor-core operand tiles - csrc/allin_dense.cu; ValueFiller.py:160-175 is the one-card analogue."""
+        from pokerrl_b200.allin import AllinEquity
+        nodes = np.nonzero(ft.kind == nat.KIND_SHOWDOWN_ALLIN)[0]
+        if nodes.size == 0:
+            return
+        spec = ft.allin_spec
+        ranks = self.t_board_ranks[torch.from_numpy(complete).to(self.device)] if complete.size else None
+        self.allin = AllinEquity(ft.rules, spec, device=self.device, ranks=ranks)
+        self._allin_nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._allin_pot = np.ascontiguousarray(ft.pot[nodes], dtype=np.float32)
+        level_of = np.searchsorted(np.asarray(ft.level_start), nodes, side="right") - 1
+        self._level_nallin = np.ascontiguousarray(np.bincount(level_of, minlength=ft.n_levels), dtype=np.int64)
+        d.level_nallin = self._level_nallin.ctypes.data
+        d.allin_nodes, d.allin_pot = self._allin_nodes.ctypes.data, self._allin_pot.ctypes.data
+        d.allin_tiles, d.allin_partial = self.allin.tiles.data_ptr(), self.allin.partial.data_ptr()
 
     @property
     def n_nodes(self):

@@ -38,7 +38,18 @@ def oracle_tree(ft):
     complete = np.nonzero((bc >= 0).sum(axis=1) == 5)[0]
     if complete.size:
         ranks[complete] = oracle_ranks(bc[complete])
-    return o2.Oracle2Tree(ft, lut.LUT_IDX_2_HOLE_CARDS, ranks, ft.board_prob, ft.board_mult, spec.sym_perm)
+    t = o2.Oracle2Tree(ft, lut.LUT_IDX_2_HOLE_CARDS, ranks, ft.board_prob, ft.board_mult, spec.sym_perm)
+    if getattr(ft, "allin_spec", None) is not None:
+        t.allin_equity = oracle_allin_equity(ft.rules, ft.allin_spec)
+    return t
+
+
+def oracle_allin_equity(rules, spec, ranks=None):
+    """float64 equity matrix of the boards of `spec` (hand strengths from the C evaluator pinned to lib_hand_eval.so)"""
+    rk = oracle_ranks(spec.boards) if ranks is None else ranks
+    w = np.asarray(spec.board_prob, np.float64) * np.asarray(spec.board_mult, np.float64)
+    hc = np.asarray(rules.get_lut_holder().LUT_IDX_2_HOLE_CARDS).astype(np.int64)
+    return o2.allin_equity_matrix(rk, w, hc, rules.N_CARDS_IN_DECK, spec.sym_perm)
 
 
 def hulh_flop_subgame(cards_per_layer, root_board=(0, 5, 10), stack=48):
