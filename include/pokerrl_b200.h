@@ -321,7 +321,7 @@ int prl_board_permute(const prl_board_game_t* g, int rows_per_board, const int64
  * All-in showdowns before the board is complete, two-card games (csrc/allin_dense.cu).  The reference enumerates the
  * missing board cards per terminal (ValueFiller.py:160-175 `_get_call_eq_preflop`, one-card games only); here the public
  * state's EQUITY MATRIX  E[h][h'] = sum over the sym_perm permutations q and the completions b of the board of
- * w_b * sign(rank_b(q(h)) - rank_b(h')) (0 where a hand is blocked or the two hands share a card) is built once, stored
+ * w_b * sign(rank_b(q(h)) - rank_b(q(h'))) (0 where a hand is blocked or the two hands share a card) is built once, stored
  * as three bf16 split planes in tcgen05 operand tiles, and every all-in terminal costs one column of a tensor-core GEMM
  * (BASELINE.json north_star: "tensor cores used only for the dense 1326x1326 Hold'em showdown equity contraction").
  *   prl_allin_equity_accumulate: ec (DEVICE double[n_range][n_range], zeroed by the caller) += sum_b weight[b] * S_b for a chunk

@@ -36,9 +36,11 @@ def sign_matrix(ranks, compat, blocked):
 
 
 def allin_equity_matrix(ranks, weight, hand_cards, n_deck, sym_perm=None):
-    """E[h][h'] = sum over the hand permutations q and the boards b of weight_b * S_b[q(h)][h'] with S_b = sign_matrix of
-    board b (float64, brute force): the value rows of an all-in showdown before the deal are K * pot / 2 * E @ reach_opp -
-    exactly what a chance node over those boards with showdown children and board_prob * board_mult = weight would give."""
+    """E[h][h'] = sum over the hand permutations q and the boards b of weight_b * S_b[q(h)][q(h')] with S_b = sign_matrix
+    of board b (float64, brute force) = the matrix of ALL boards of the orbits.  The value rows of an all-in showdown before
+    the deal are K * pot / 2 * E @ reach_opp - for suit-symmetric reach rows (the isomorphism contract of
+    game/holdem_boards.py) exactly what a chance node over those boards with showdown children and board_prob * board_mult =
+    weight gives."""
     R = ranks.shape[1]
     inc = np.zeros((R, n_deck))
     for k in range(hand_cards.shape[1]):
@@ -49,7 +51,7 @@ def allin_equity_matrix(ranks, weight, hand_cards, n_deck, sym_perm=None):
         ec += weight[b] * sign_matrix(ranks[b], compat, ranks[b] < 0)
     if sym_perm is None:
         return ec
-    return sum(ec[np.asarray(pm, np.int64)] for pm in sym_perm)
+    return sum(ec[np.ix_(np.asarray(pm, np.int64), np.asarray(pm, np.int64))] for pm in sym_perm)
 
 
 class Oracle2Tree:

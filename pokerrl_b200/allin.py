@@ -3,7 +3,7 @@ rows on the tensor cores - host side of csrc/allin_dense.cu.
 
 Reference: ValueFiller.py:160-175 (`_get_call_eq_preflop`) enumerates the missing board per terminal for one-card games;
 for two-card hands the sum over the boards is strategy-independent and is folded into one matrix
-    E[h][h'] = sum_q sum_b prob_b * mult_b * sign(rank_b(q(h)) - rank_b(h'))
+    E[h][h'] = sum_q sum_b prob_b * mult_b * sign(rank_b(q(h)) - rank_b(q(h')))
 (q: suit permutations of the isomorphism contract, game/holdem_boards.py).  No CPU fallback: every step is a kernel."""
 import ctypes as C
 

@@ -3,7 +3,7 @@
 // Reference: ValueFiller.py:160-175 (`_get_call_eq_preflop`, one-card games: the missing board card is enumerated per
 // terminal and the per-board showdown rows of ValueFiller.py:127-158 are averaged).  For two-card hands the enumeration is
 // C(48,5) boards per terminal and iteration; the sum over boards does not depend on the strategy, so it is done ONCE:
-//     E[h][h'] = sum_q sum_b w_b * sign(rank_b(q(h)) - rank_b(h'))        (0: a hand blocked by b, or h and h' share a card)
+//     E[h][h'] = sum_q sum_b w_b * sign(rank_b(q(h)) - rank_b(q(h')))     (0: a hand blocked by b, or h and h' share a card)
 // (q: the suit permutations of the isomorphism contract, holdem_boards.py; w_b = deal probability x weight in the parent's
 // sum) and an all-in terminal's value row is  K * pot / 2 * E @ reach_opp  - a dense real 1326 x 1326 contraction, the one
 // place of this path where tensor cores are the right tool (BASELINE.json north_star).
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) allin_accum_kernel(const int32_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------- equity matrix, step 2
-// E[h][h'] = sum_q Ec[perm_q[h]][h'] (no permutations: Ec), 0 for hands that share a card or lie in the padding; three bf16
+// E[h][h'] = sum_q Ec[perm_q[h]][perm_q[h']] (no permutations: Ec), 0 for hands that share a card or lie in the padding; three bf16
 // planes into the operand tiles: plane s of tile (mt, kb) starts at ((mt * KB + kb) * 3 + s) * 8192 elements.
 __global__ void __launch_bounds__(256) allin_tiles_kernel(const double* __restrict__ ec, int R, const int8_t* __restrict__ hand_cards,
                                                           const int16_t* __restrict__ sym_perm, int n_sym, int KB,
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) allin_tiles_kernel(const double* __restri
         const int a1 = hand_cards[2 * h], a2 = hand_cards[2 * h + 1], b1 = hand_cards[2 * g], b2 = hand_cards[2 * g + 1];
         if (a1 != b1 && a1 != b2 && a2 != b1 && a2 != b2) {
             if (n_sym > 1) {
-                for (int q = 0; q < n_sym; ++q) e += ec[(size_t)sym_perm[(size_t)q * R + h] * R + g];
+                for (int q = 0; q < n_sym; ++q) e += ec[(size_t)sym_perm[(size_t)q * R + h] * R + sym_perm[(size_t)q * R + g]];
             } else {
                 e = ec[(size_t)h * R + g];
             }

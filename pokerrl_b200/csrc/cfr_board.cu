@@ -53,15 +53,25 @@ static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move mult
 #define PRL_BV_RED 1         // chance sums by 64-bit RED instead of load + add + store
 #endif
 #ifndef PRL_BV_P1PIPE
-#define PRL_BV_P1PIPE 1      // P1 rows: only the first position is requested one unit ahead, the others pipelined inside P1
+#define PRL_BV_P1PIPE 1      // P1 rows: 1 / 2 = only the first (two) position(s) requested one unit ahead, the rest inside P1; 0 = all three
 #endif
 #ifndef PRL_BV_FOLDLIN
 #define PRL_BV_FOLDLIN 1     // update form: card-row sums of the fold vectors from the showdown vectors' row totals (linearity)
 #endif
-#ifndef PRL_BV_SERIALSCAN
-#define PRL_BV_SERIALSCAN 0  // main prefix sums: one warp per vector, 35 consecutive positions per lane, no cross-warp stage
-#endif                       // (measured: +1 % alone, -5 % on top of the other three - seven idle warps cost more than the shuffles)
-constexpr bool kVRed = PRL_BV_RED, kVP1Pipe = PRL_BV_P1PIPE, kVFoldLin = PRL_BV_FOLDLIN, kVSerialScan = PRL_BV_SERIALSCAN;
+#ifndef PRL_BV_SCAN7
+#define PRL_BV_SCAN7 0       // main prefix sums by five warps (the lighter card-row group), seven consecutive positions per thread
+#endif                       // (measured: 89.7 vs 92.4 it/s - idle warps cost more than the shuffles they save)
+#ifndef PRL_BV_ERT
+#define PRL_BV_ERT 1         // card-row prefix arrays entry-major (Er[v][k][card]) instead of card-major: fewer store conflicts in P2a
+#endif
+#ifndef PRL_BV_P3BAL
+#define PRL_BV_P3BAL 0       // P3: the 313 positions of the third pass spread over all twelve warps (27 lanes each)
+#endif                       // (measured: 91.0 vs 92.2 it/s)
+#ifndef PRL_BV_SPLITB3
+#define PRL_BV_SPLITB3 0     // the single-warp stage between B2 and B3 spread over nine warps (one vector / fold vector each)
+#endif                       // (measured: 89.0 vs 92.2 it/s)
+constexpr int kVP1Pipe = PRL_BV_P1PIPE;
+constexpr bool kVRed = PRL_BV_RED, kVFoldLin = PRL_BV_FOLDLIN, kVScan7 = PRL_BV_SCAN7, kVSplitB3 = PRL_BV_SPLITB3, kVErT = PRL_BV_ERT, kVP3Bal = PRL_BV_P3BAL;
 
 constexpr int kThreads = 384;  // 12 warps; 3 strength positions per thread (3 * 384 = 1152 >= 1081: 94 % of the lanes busy)
 constexpr int kPerThread = 3;
@@ -284,16 +294,15 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     // P1 inputs of the thread's three strength positions (opponent rows + trunk reach).  kVP1Pipe: only the first position
     // is requested one unit ahead (8 registers live across the unit's last barrier - 24 spilled to local memory and made the
     // warp wait for the loads there); the other two are requested inside P1, one position ahead of their use.
-    constexpr int kP1Ahead = kVP1Pipe ? 1 : kPerThread;
+    constexpr int kP1Ahead = kVP1Pipe ? kVP1Pipe : kPerThread;
     float p1_g[kP1Ahead][NOPP], p1_x0[kP1Ahead];
     auto p1_load_k = [&](int jj, const int16_t* sh_jj, int k, float (&g)[NOPP], float& x0) {
-        const int i = tid + k * kThreads;
-        if (i < kLive) {
-            const float* rows = tab_opp + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb + i;
+        // lanes past the last hand read the last hand's values (never used): unconditional loads keep the arrays in registers
+        const int i = min(tid + k * kThreads, kLive - 1);
+        const float* rows = tab_opp + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb + i;
 #pragma unroll
-            for (int r = 0; r < NOPP; ++r) g[r] = ld_stream(rows + (size_t)r * kLdb);
-            x0 = __ldg(a.trunk_reach_opp + sh_jj[i]);
-        }
+        for (int r = 0; r < NOPP; ++r) g[r] = ld_stream(rows + (size_t)r * kLdb);
+        x0 = __ldg(a.trunk_reach_opp + sh_jj[i]);
     };
     auto p1_load = [&](int jj, const int16_t* sh_jj) {
 #pragma unroll
@@ -349,12 +358,18 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 });
             }
         };
-        if constexpr (kVP1Pipe) {
+        if constexpr (kVP1Pipe == 1) {
             float gB[NOPP], gC[NOPP], xB = 0.0f, xC = 0.0f;
             p1_load_k(j, sh, 1, gB, xB);
             p1_hand(0, p1_g[0], p1_x0[0]);
             p1_load_k(j, sh, 2, gC, xC);
             p1_hand(1, gB, xB);
+            p1_hand(2, gC, xC);
+        } else if constexpr (kVP1Pipe == 2) {  // the third position's rows have two hands' worth of work to arrive
+            float gC[NOPP], xC = 0.0f;
+            p1_load_k(j, sh, 2, gC, xC);
+            p1_hand(0, p1_g[0], p1_x0[0]);
+            p1_hand(1, p1_g[1], p1_x0[1]);
             p1_hand(2, gC, xC);
         } else {
 #pragma unroll
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // fold vectors: the row's mass cs[f][lc].  Two groups of 47 quads share the nine vectors (SD 0-2 + fold 0-1 | SD 3-4 +
         // fold 2-3); the other threads start on the main scans, which only read S as well.
         mbar_wait(&bars[2], it & 1);
-        constexpr int NLEG = kVSerialScan ? 1 : NSD;  // state of the thread-per-three-positions scan (legacy variant)
+        constexpr int NLEG = kVScan7 ? 1 : NSD;  // registers of the thread-per-three-positions scan (legacy variant)
         float a0[NLEG], a1[NLEG], a2[NLEG];
         double pre[NLEG];
         constexpr int kQuadThreads = kLiveCards * 4;  // 188
@@ -410,10 +425,10 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 if (q >= 2) sc += tt;
                 const float half = 0.5f * __shfl_sync(qmask, sc, 3, 4);
                 const float off = (sc - run) - half;
-                float* row = Er + v * kErVec + lc * kErStride + q * kRowSeg;
+                float* row = Er + v * kErVec + (kVErT ? q * kRowSeg * kErStride + lc : lc * kErStride + q * kRowSeg);
 #pragma unroll
                 for (int e = 0; e < kRowSeg; ++e)
-                    if (row_live && q * kRowSeg + e < kErStride) row[e] = off + inc[e];
+                    if (row_live && q * kRowSeg + e < kErStride) row[kVErT ? e * kErStride : e] = off + inc[e];
             }
 #pragma unroll 1
             for (int f = 2 * grp; f < (kLin ? 0 : 2 * grp + 2); ++f) {  // kLin: nothing to gather for the fold vectors
@@ -430,33 +445,32 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // ------------------------------------------------------------------------------------------ P2b: main scans, part 1
         // centred exclusive prefix sums over the strength order: E[k] = (mass of the k weakest hands) - total / 2, k = 0 ..
         // 1081, sums in double (the showdown value is a difference of two prefixes).
-        // kVSerialScan: ONE warp per vector (warps 7..11, the lighter card-row group), lane l owns the 35 consecutive positions
-        // 35 l .. 35 l + 34 (odd stride: conflict-free): a serial pass for the lane totals, one warp scan, and after B2 a second
-        // serial pass that writes the prefixes in place - a third of the instructions of the three-positions-per-thread scan,
-        // no cross-warp stage (its single-warp section made eleven warps wait at a barrier of its own).
-        constexpr int kScanWarp0 = 7, kScanChunk = 35;
-        static_assert(kScanWarp0 + NSD <= kWarps && 32 * kScanChunk > kLive + 1 && (kScanChunk & 1), "scan geometry");
-        const bool scan_warp = kVSerialScan && warp >= kScanWarp0 && warp < kScanWarp0 + NSD;
-        double scan_base = 0.0;
-        if constexpr (kVSerialScan) {
+        // kVScan7: by the five warps 7..11 only - the card-row group with two vectors instead of three, so the two groups
+        // finish P2 together - thread t owns the seven consecutive positions 7 t .. 7 t + 6 (odd stride: conflict-free):
+        // 5 / 12 of the shuffles of the thread-per-three-positions scan, and after B2 every scan warp adds the totals of the
+        // warps below it itself (the single-warp scan of the warp totals and its barrier are gone).
+        constexpr int kScanWarp0 = 7, kScanWarps = kWarps - kScanWarp0, kScanPer = 7;
+        static_assert(kScanWarps * 32 * kScanPer > kLive + 1 && (kScanPer & 1), "scan geometry");
+        const bool scan_warp = kVScan7 && warp >= kScanWarp0;
+        double pre7[kVScan7 ? NSD : 1];
+        if constexpr (kVScan7) {
             if (scan_warp) {
-                const float* Sv = S + (warp - kScanWarp0) * kLdb;
-                const int p0 = lane * kScanChunk;
-                double tot = 0.0;
-#pragma unroll 7
-                for (int e = 0; e < kScanChunk; ++e) {
-                    const int p = p0 + e;
-                    const float xv = (p < kLive) ? Sv[p] : 0.0f;
-                    tot += (double)xv;
-                }
-                double incw = tot;
+                const int b0 = kScanPer * (tid - kScanWarp0 * 32);
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double tt = __shfl_up_sync(0xffffffffu, incw, o);
-                    if (lane >= o) incw += tt;
+                for (int v = 0; v < NSD; ++v) {
+                    const float* Sv = S + v * kLdb;
+                    double loc = 0.0;
+#pragma unroll
+                    for (int e = 0; e < kScanPer; ++e) loc += (b0 + e < kLive) ? (double)Sv[b0 + e] : 0.0;
+                    double incw = loc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double tt = __shfl_up_sync(0xffffffffu, incw, o);
+                        if (lane >= o) incw += tt;
+                    }
+                    pre7[v] = incw - loc;  // exclusive within the warp
+                    if (lane == 31) wsum[v * 16 + (warp - kScanWarp0)] = incw;
                 }
-                const double total = __shfl_sync(0xffffffffu, incw, 31);
-                scan_base = (incw - tot) - 0.5 * total;
             }
         } else {
             const int b0 = 3 * tid;
@@ -480,20 +494,26 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // P3 inputs of the first strength position: requested here, consumed after the prefix sums are written back
         const float mult = __ldg(G.board_mult + j);
         const double fx = (double)mult * a.fx_scale;
-        const float* own_rows = tab_own + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
-        float* reg_rows = G.regret + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
-        float* avg_rows = G.avg + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb + tid;
+        const float* own_rows = tab_own + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb;
+        float* reg_rows = G.regret + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb;
+        float* avg_rows = G.avg + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb;
+        // strength position of the thread's k-th hand of P3.  kVP3Bal: the last pass has only 1081 - 768 = 313 positions - ten
+        // warps' worth, two warps would idle at the unit's last barrier - so every warp takes 27 of them
+        constexpr int kP3Last = (kLive - 2 * kThreads + kWarps - 1) / kWarps;  // 27
+        auto p3_pos = [&](int k) -> int {
+            if (kVP3Bal && k == 2) return (lane < kP3Last) ? 2 * kThreads + warp * kP3Last + lane : kLdb;
+            return tid + k * kThreads;
+        };
         float gA[NOWN], aA[NOWN], gB[NOWN], aB[NOWN];
         auto p3_load = [&](int k, float (&g)[NOWN], float (&av)[NOWN]) {
-            if (tid + k * kThreads < kLive) {
+            const int i = min(p3_pos(k), kLive - 1);  // unconditional (see p1_load_k)
 #pragma unroll
-                for (int r = 0; r < NOWN; ++r) g[r] = ld_stream(own_rows + (size_t)r * kLdb + k * kThreads);
-            }
+            for (int r = 0; r < NOWN; ++r) g[r] = ld_stream(own_rows + (size_t)r * kLdb + i);
 #pragma unroll
             for (int r = 0; r < NOWN; ++r) av[r] = 0.0f;
-            if (read_avg && tid + k * kThreads < kLive) {
+            if (read_avg) {
 #pragma unroll
-                for (int r = 0; r < NOWN; ++r) av[r] = ld_stream(avg_rows + (size_t)r * kLdb + k * kThreads);
+                for (int r = 0; r < NOWN; ++r) av[r] = ld_stream(avg_rows + (size_t)r * kLdb + i);
             }
         };
         p3_load(0, gA, aA);
@@ -530,18 +550,28 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             if (lane < kLiveCards) cs[f * kRowPad + lane] = (float)c0;  // float copies for the per-hand epilogue
             if (lane + 32 < kLiveCards) cs[f * kRowPad + lane + 32] = (float)c1;
         };
-        if constexpr (kVSerialScan) {
-            if (scan_warp) {  // second serial pass: the prefixes in place
-                float* Sv = S + (warp - kScanWarp0) * kLdb;
-                const int p0 = lane * kScanChunk;
-                double run = scan_base;
-#pragma unroll 7
-                for (int e = 0; e < kScanChunk; ++e) {
-                    const int p = p0 + e;
-                    if (p <= kLive) {
-                        const float xv = (p < kLive) ? Sv[p] : 0.0f;
-                        Sv[p] = (float)run;
-                        run += (double)xv;
+        if constexpr (kVScan7) {
+            if (scan_warp) {  // offsets from the warp totals (written before B2), then the prefixes in place
+                const int b0 = kScanPer * (tid - kScanWarp0 * 32), sw = warp - kScanWarp0;
+#pragma unroll
+                for (int v = 0; v < NSD; ++v) {
+                    double below = 0.0, total = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kScanWarps; ++w) {
+                        const double t = wsum[v * 16 + w];
+                        total += t;
+                        below += (w < sw) ? t : 0.0;
+                    }
+                    float* Sv = S + v * kLdb;
+                    double run = (pre7[v] + below) - 0.5 * total;
+#pragma unroll
+                    for (int e = 0; e < kScanPer; ++e) {
+                        const int p = b0 + e;
+                        if (p <= kLive) {
+                            const float xv = (p < kLive) ? Sv[p] : 0.0f;
+                            Sv[p] = (float)run;
+                            run += (double)xv;
+                        }
                     }
                 }
             } else if (warp < NF) {
@@ -550,19 +580,29 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 });
             }
         } else {
-            if (warp == 0) {
+            auto warp_totals_scan = [&](int v) {  // exclusive scan of the 12 warp totals of vector v
+                const double w = (lane < kWarps) ? wsum[v * 16 + lane] : 0.0;
+                double sc = w;
 #pragma unroll
-                for (int v = 0; v < NLEG; ++v) {  // exclusive scan of the 12 warp totals
-                    const double w = (lane < kWarps) ? wsum[v * 16 + lane] : 0.0;
-                    double sc = w;
-#pragma unroll
-                    for (int o = 1; o < 16; o <<= 1) {
-                        const double tt = __shfl_up_sync(0xffffffffu, sc, o);
-                        if (lane >= o) sc += tt;
-                    }
-                    const double total = __shfl_sync(0xffffffffu, sc, kWarps - 1);
-                    if (lane < kWarps) wexc[v * 16 + lane] = (sc - w) - 0.5 * total;
+                for (int o = 1; o < 16; o <<= 1) {
+                    const double tt = __shfl_up_sync(0xffffffffu, sc, o);
+                    if (lane >= o) sc += tt;
                 }
+                const double total = __shfl_sync(0xffffffffu, sc, kWarps - 1);
+                if (lane < kWarps) wexc[v * 16 + lane] = (sc - w) - 0.5 * total;
+            };
+            if constexpr (kVSplitB3) {  // nine short chains side by side instead of two long ones
+                static_assert(NLEG + NF <= kWarps, "one warp per vector");
+                if (warp < NLEG) {
+                    warp_totals_scan(warp);
+                } else if (warp < NLEG + NF) {
+                    static_for<0, NF>([&](auto F) {
+                        if (warp - NLEG == decltype(F)::value) fold_finish(F);
+                    });
+                }
+            } else if (warp == 0) {
+#pragma unroll
+                for (int v = 0; v < NLEG; ++v) warp_totals_scan(v);
             } else if (warp == 1) {
                 static_for<0, NF>([&](auto F) { fold_finish(F); });
             }
@@ -583,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
 
         // ------------------------------------------------------------------------------------------ P3: values, bottom-up
         auto p3_hand = [&](int k, const float (&gown)[NOWN], const float (&av)[NOWN]) {
-            const int i = tid + k * kThreads;
+            const int i = p3_pos(k);
             const uint64_t w = rec[i];
             const int hand = sh[i];
             long long* wacc = wp + hand;
@@ -594,8 +634,9 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             }
             const int gs = (int)(w & 0x7ffu), ge = (int)((w >> 11) & 0x7ffu);
             const int lc1 = (int)((w >> 22) & 0x3fu), lc2 = (int)((w >> 28) & 0x3fu);
-            const int o1 = lc1 * kErStride + (int)((w >> 34) & 0x3fu), o1e = o1 + (int)((w >> 40) & 0x3fu);
-            const int o2 = lc2 * kErStride + (int)((w >> 46) & 0x3fu), o2e = o2 + (int)((w >> 52) & 0x3fu);
+            const int k1 = (int)((w >> 34) & 0x3fu), t1 = (int)((w >> 40) & 0x3fu), k2 = (int)((w >> 46) & 0x3fu), t2 = (int)((w >> 52) & 0x3fu);
+            const int o1 = kVErT ? k1 * kErStride + lc1 : lc1 * kErStride + k1, o1e = o1 + (kVErT ? t1 * kErStride : t1);
+            const int o2 = kVErT ? k2 * kErStride + lc2 : lc2 * kErStride + k2, o2e = o2 + (kVErT ? t2 * kErStride : t2);
             float e[SH::N], br[EVAL ? SH::N : 1];
             // terminal rows (ValueFiller.py:103-158): ev = equity * K * pot / 2, the folder loses
             static_for<0, SH::N>([&](auto I) {
@@ -652,11 +693,11 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                             for (int c = 0; c < A; ++c) g[c] = fmaxf((e[fc + c] - v) + g[c], 0.0f);  // CFRPlus.py:37-41
                             node_strategy<A>(g, 0, s);
 #pragma unroll
-                            for (int c = 0; c < A; ++c) st_stream(reg_rows + (size_t)(r0 + c) * kLdb + k * kThreads, g[c]);
+                            for (int c = 0; c < A; ++c) st_stream(reg_rows + (size_t)(r0 + c) * kLdb + i, g[c]);
                             if (do_avg) {  // CFRPlus.py:65-87 (not reach-weighted)
 #pragma unroll
                                 for (int c = 0; c < A; ++c)
-                                    st_stream(avg_rows + (size_t)(r0 + c) * kLdb + k * kThreads, a.m_old * av[r0 + c] + a.m_new * s[c]);
+                                    st_stream(avg_rows + (size_t)(r0 + c) * kLdb + i, a.m_old * av[r0 + c] + a.m_new * s[c]);
                             }
                         }
                     }
@@ -677,8 +718,8 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         p3_load(1, gB, aB);
         p3_hand(0, gA, aA);
         p3_load(2, gA, aA);
-        if (tid + kThreads < kLive) p3_hand(1, gB, aB);
-        if (tid + 2 * kThreads < kLive) p3_hand(2, gA, aA);
+        if (p3_pos(1) < kLive) p3_hand(1, gB, aB);
+        if (p3_pos(2) < kLive) p3_hand(2, gA, aA);
         // next unit's P1 inputs: requested before the barrier below, consumed after it (the other table buffer is long there)
         if (jn < nb) {
             mbar_wait(&bars[buf ^ 1], ((it + 1) >> 1) & 1);

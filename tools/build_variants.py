@@ -10,13 +10,18 @@ sys.path.insert(0, ROOT)
 from pokerrl_b200.csrc import build as B  # noqa: E402
 
 VARIANTS = {
-    "base": dict(RED=0, P1PIPE=0, FOLDLIN=0, SERIALSCAN=0),
-    "red": dict(RED=1, P1PIPE=0, FOLDLIN=0, SERIALSCAN=0),
-    "p1pipe": dict(RED=0, P1PIPE=1, FOLDLIN=0, SERIALSCAN=0),
-    "foldlin": dict(RED=0, P1PIPE=0, FOLDLIN=1, SERIALSCAN=0),
-    "serialscan": dict(RED=0, P1PIPE=0, FOLDLIN=0, SERIALSCAN=1),
-    "all": dict(RED=1, P1PIPE=1, FOLDLIN=1, SERIALSCAN=1),
-    "all_noscan": dict(RED=1, P1PIPE=1, FOLDLIN=1, SERIALSCAN=0),
+    "base": dict(RED=0, P1PIPE=0, FOLDLIN=0, SCAN7=0, SPLITB3=0),
+    "red": dict(RED=1, P1PIPE=0, FOLDLIN=0, SCAN7=0, SPLITB3=0),
+    "p1pipe": dict(RED=0, P1PIPE=1, FOLDLIN=0, SCAN7=0, SPLITB3=0),
+    "foldlin": dict(RED=0, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0),
+    "noscan": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0),
+    "scan7": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=1, SPLITB3=0),
+    "splitb3": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=1),
+    "ert": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
+    "splitb3_ert": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=1, ERT=1),
+    "ert_p1a2": dict(RED=1, P1PIPE=2, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
+    "p3bal": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, P3BAL=1),
+    "splitb3_ert_p3bal": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=1, ERT=1, P3BAL=1),
 }
 
 
