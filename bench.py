@@ -351,10 +351,16 @@ def main_fhp(a, rank, world, local_rank):
     K = a.steps if a.steps is not None else 200
     W = max(3, a.warmup if a.warmup is not None else 5)
     nb_used = a.fhp_boards or N_CLASSES
-    cfg = {"workload": "Flop5Holdem CFR+ delay 0, full game: 134 459 suit-isomorphism classes of the 2 598 960 five-card boards, "
+    algo_label = {"CFRPlus": "CFR+", "LinearCFR": "Linear CFR", "VanillaCFR": "Vanilla CFR"}[a.algo]
+    cfg = {"workload": "Flop5Holdem %s%s, full game: 134 459 suit-isomorphism classes of the 2 598 960 five-card boards, "
                        "range 1326, stack 20000, exact BR (current+average) every %d iterations%s"
-                       % (a.eval_every, " [DEBUG SUBSET: first %d classes]" % a.fhp_boards if a.fhp_boards else "")}
+                       % (algo_label, " delay 0" if a.algo == "CFRPlus" else "", a.eval_every,
+                          " [DEBUG SUBSET: first %d classes]" % a.fhp_boards if a.fhp_boards else "")}
     ncpu = os.cpu_count() or 1
+    if a.impl == "reference" and a.algo != "CFRPlus":
+        if rank == 0:
+            emit({"impl": "reference", "unavailable": "the CPU arm of the fhp workload times CFR+ (the headline metric)"})
+        return
     if a.impl == "reference":
         if rank != 0:
             return
@@ -392,7 +398,7 @@ def main_fhp(a, rank, world, local_rank):
         spec = fhp_subset(spec, a.fhp_boards)
     t_spec = time.perf_counter() - t0
     t0 = time.perf_counter()
-    s = BoardCFRSolver(g, args, spec, device=dev, rank=rank, world=world)
+    s = BoardCFRSolver(g, args, spec, algo=a.algo, device=dev, rank=rank, world=world)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
     L = s.L
@@ -449,6 +455,7 @@ def main_fhp(a, rank, world, local_rank):
         for p in (0, 1):
             e0, e1 = ev_pair()
             e0.record()
+            s._pending[1 - p] = 1.0 if a.algo != "CFRPlus" else 0.0  # Vanilla / Linear: the sweep also adds the opponent's average
             s._sweep_begin(s.bufs, p, False, 0, 0)
             e1.record()
             torch.cuda.synchronize()
@@ -541,15 +548,17 @@ def main_fhp(a, rank, world, local_rank):
         del part
 
     # --- e2e: the user-facing call (CFRPlus facade: iteration() + logging through ChiefBase, results read on the host)
-    from pokerrl_b200.cfr.CFRPlus import CFRPlus
+    import importlib
+    CFRPlus = getattr(importlib.import_module("pokerrl_b200.cfr." + a.algo), a.algo)  # CFRPlus / LinearCFR / VanillaCFR facade
     from pokerrl_b200.game import games
     from pokerrl_b200.rl.base_cls.workers.ChiefBase import ChiefBase
     del s
     torch.cuda.empty_cache()
     chief = ChiefBase(t_prof=None)
     with contextlib.redirect_stdout(io.StringIO()):
-        cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=games.Flop5Holdem, agent_bet_set=[1.0], delay=0,
-                      eval_every=a.eval_every, device=dev, board_spec=spec)
+        kw = dict(delay=0) if a.algo == "CFRPlus" else {}
+        cfr = CFRPlus(name="bench", chief_handle=chief, game_cls=games.Flop5Holdem, agent_bet_set=[1.0],
+                      eval_every=a.eval_every, device=dev, board_spec=spec, **kw)
     for _ in range(W):
         cfr.iteration()
     cfr.reset()
@@ -570,7 +579,7 @@ def main_fhp(a, rank, world, local_rank):
             dist.destroy_process_group()
         return
     out = {
-        "metric": "CFR+ iterations/s", "value": K / (max_ms * 1e-3), "unit": "iterations/s", "n_gpus": world, "steps": K,
+        "metric": algo_label + " iterations/s", "value": K / (max_ms * 1e-3), "unit": "iterations/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": it_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (deterministic game tree, no dataset)",
         "config": dict(cfg, boards_per_rank=s_n_boards(nb_used, rank, world), engine="board-resident (pokerrl_b200/board_engine.py)",
@@ -589,7 +598,7 @@ def main_fhp(a, rank, world, local_rank):
     }
     if invariance is not None:
         out["shard_invariance"] = invariance
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.algo == "CFRPlus":
         n_it = 6
         sec, threads, expl = run_cpu_fhp(FHP_CPU_BOARDS, n_it, ncpu)
         out["matched_instance"].update(cpu_iterations_per_s=1.0 / sec, cpu_threads=threads, same_config=True,
@@ -632,6 +641,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fhp", choices=WORKLOADS)
     ap.add_argument("--eval-every", type=int, default=20)
+    ap.add_argument("--algo", default="CFRPlus", choices=["CFRPlus", "LinearCFR", "VanillaCFR"],
+                    help="fhp workload: the algorithm the board engine runs (the headline metric is CFRPlus)")
     ap.add_argument("--fhp-boards", type=int, default=0, help="debug: only the first n isomorphism classes")
     ap.add_argument("--hulh-turns", type=int, default=0, help="hulh: only the first n turn cards (memory: the full 49 need >= 2 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -27,7 +27,7 @@ typedef void* prl_stream_t; /* cudaStream_t */
 
 /* bumped whenever a struct below changes; prl_abi_version() returns the value the library was built with
    (2: prl_tree_t gained board_hand_rec / node_rec2 / work_rec2 / level_nfold; 3: board engine, legacy LUT natives;
-    4: prl_tree_t gained the all-in terminals of two-card games: level_nallin / allin_nodes / allin_pot / allin_tiles /
+    4: prl_board_sweep / prl_board_trunk take the algorithm; prl_tree_t gained the all-in terminals of two-card games: level_nallin / allin_nodes / allin_pot / allin_tiles /
     allin_partial) */
 #define PRL_ABI_VERSION 4
 
@@ -267,12 +267,17 @@ int prl_board_shape_ok(const prl_board_game_t* g);     /* 1 iff kind / parent / 
 int prl_board_build_tables(const int32_t* ranks, const uint64_t* board_mask, const int8_t* hand_cards, int n_boards,
                            void* blob, prl_stream_t stream);
 
-/* One sweep over all boards for seat p.  eval == 0: CFR+ update of p's post-deal rows (iteration iter, averaging delay
- * `delay`); eval != 0: values and best-response values of p with the strategies of p / the opponent taken from
- * src_own / src_opp (0 = regret matching of `regret`, 1 = rows of `avg`).  trunk_reach_opp = DEVICE float[ld]: reach row
- * of the opponent at the chance node.  Leaves the fixed-point sums in g->w_total (the arrays it produces are zeroed first). */
+/* One sweep over all boards for seat p.  eval == 0: update of p's post-deal rows by `algo` (PRL_ALGO_*; iteration iter,
+ * CFR+ averaging delay `delay`); eval != 0: values and best-response values of p with the strategies of p / the opponent
+ * taken from src_own / src_opp (0 = regret matching of `regret`, 1 = rows of `avg` as they are (CFR+ average), 2 = rows of
+ * `avg` normalised (the reach-weighted sums of Vanilla / Linear CFR)).  trunk_reach_opp = DEVICE float[ld]: reach row of the
+ * opponent at the chance node.  Leaves the fixed-point sums in g->w_total (the arrays it produces are zeroed first).
+ * Vanilla / Linear CFR (VanillaCFR.py:54-60, LinearCFR.py:53-59): the average is the sum of strategy x own reach x weight with
+ * the reach under the NEW strategy, trunk included - known only after the seat's trunk update.  The contribution of the
+ * OPPONENT's last update is therefore added by this sweep (defer_w = its weight, 0 = none pending), which walks those rows
+ * anyway; p1_only != 0 does nothing else (flush before the average strategy is evaluated or exported). */
 int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int src_own, int src_opp, const float* trunk_reach_opp,
-                    int iter, int delay, prl_stream_t stream);
+                    int iter, int delay, int algo, float defer_w, int p1_only, prl_stream_t stream);
 
 /* out[a][h] = 2^-frac_bits * sum over the n_sym suit permutations of w_total[a][perm(h)] (n_sym <= 1: no symmetrisation),
  * a < n_arr: the chance node's rows for the trunk sweep (after an all-reduce of w_total across GPUs, if sharded). */
@@ -305,7 +310,7 @@ typedef struct {
  * peers == NULL: g->w_total already holds the global sums (single GPU, or all-reduced by the caller). */
 int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, int eval, int p, int n_sym, const int16_t* sym_perm, int iter,
                     int delay, float* out_expl, const int64_t* const* peers, int n_peers, int64_t peer_offset, int64_t* w_scratch,
-                    prl_stream_t stream);
+                    int algo, prl_stream_t stream);
 
 /* Strength-ordered rows <-> natural-order rows.  row_src / row_dst = DEVICE int64[rows_per_board][2] {row on board 0,
  * stride per board} in the strength-ordered table and in a natural-order table of stride ld. */

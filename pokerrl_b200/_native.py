@@ -141,12 +141,13 @@ def lib():
     L.prl_board_rows.restype = C.c_int
     L.prl_board_shape_ok.argtypes = [gp]
     L.prl_board_build_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-    L.prl_board_sweep.argtypes = [gp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.prl_board_sweep.argtypes = [gp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                  C.c_void_p]
     L.prl_board_collect.argtypes = [gp, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.prl_board_permute.argtypes = [gp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p]
     L.prl_board_trunk.argtypes = [gp, C.POINTER(PrlTrunk), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                  C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+                                  C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     L.prl_board_trunk.restype = C.c_int
     for f in ("prl_board_layout", "prl_board_grid", "prl_board_shape_ok", "prl_board_build_tables", "prl_board_sweep",
               "prl_board_collect", "prl_board_permute"):

@@ -21,7 +21,8 @@ from pokerrl_b200.game.flat_tree import FlatTree
 from pokerrl_b200.game.holdem_boards import BoardSpec
 from pokerrl_b200.solver import DeviceTree, TreeBuffers, TreeOps, _require_cuda
 
-SRC_REGRET, SRC_AVG = 0, 1
+SRC_REGRET, SRC_AVG, SRC_AVG_SUM = 0, 1, 2
+ALGOS = {"VanillaCFR": nat.ALGO_VANILLA, "CFRPlus": nat.ALGO_CFR_PLUS, "LinearCFR": nat.ALGO_LINEAR}
 
 
 def board_layout():
@@ -37,7 +38,7 @@ def _stream(dev):
 
 def supports(game_cls, env_args, algo):
     """True iff the game's abstract tree is one pre-deal trunk + one chance layer + the compiled post-deal shape"""
-    if algo != "CFRPlus" or game_cls.RULES.N_HOLE_CARDS != 2 or game_cls.RULES.N_CARDS_IN_DECK != 52:
+    if algo not in ALGOS or game_cls.RULES.N_HOLE_CARDS != 2 or game_cls.RULES.N_CARDS_IN_DECK != 52:
         return False
     if game_cls.RULES.N_FLOP_CARDS != 5 or os.environ.get("PRL_ENGINE", "board") != "board":
         return False
@@ -67,13 +68,17 @@ def _fill_shape(g, st):
 class BoardCFRSolver:
     def __init__(self, game_cls, env_args, board_spec=None, algo="CFRPlus", delay=0, device=None, rank=0, world=1,
                  group=None, grid=0, reduce_fn=None):
-        if algo != "CFRPlus":
-            raise ValueError("the board engine implements CFR+ (use the level engine for Vanilla / Linear CFR)")
+        if algo not in ALGOS:
+            raise ValueError("unknown algorithm %r" % (algo,))
         self.device = _require_cuda(device)
         self.rank, self.world, self.group = int(rank), int(world), group
         # cross-rank sum of the fixed-point chance sums, in place; default: torch.distributed all-reduce when world > 1
         self._reduce_fn = reduce_fn
-        self.algo_name, self.algo, self.delay = algo, nat.ALGO_CFR_PLUS, int(delay)
+        self.algo_name, self.algo = algo, ALGOS[algo]
+        self.delay = int(delay) if algo == "CFRPlus" else 0
+        # Vanilla / Linear CFR: weight of the average-strategy contribution of each seat's last update that the post-deal rows
+        # have not received yet (it is added by the next sweep that walks those rows: csrc/cfr_board.cu, DEFER)
+        self._pending = [0.0, 0.0]
         self.game_cls, self.env_args = game_cls, env_args
         rules = game_cls.RULES
         spec = board_spec if board_spec is not None else BoardSpec.full_game(rules)
@@ -218,7 +223,7 @@ class BoardCFRSolver:
             peers, n_peers, off = C.c_void_p(self._peer_ptrs.data_ptr()), self.world, self._gen * 4 * self.R
         nat.call("prl_board_trunk", C.byref(self.g), C.byref(self._trunk_desc(bufs, modes)), int(evaluate), p, self.n_sym,
                  C.c_void_p(self.t_sym.data_ptr()) if self.n_sym else None, self.iter_counter, self.delay,
-                 C.c_void_p(self._expl.data_ptr()), peers, n_peers, off, C.c_void_p(self.w_scratch.data_ptr()),
+                 C.c_void_p(self._expl.data_ptr()), peers, n_peers, off, C.c_void_p(self.w_scratch.data_ptr()), self.algo,
                  _stream(self.device))
 
     def _next_generation(self):
@@ -252,8 +257,20 @@ class BoardCFRSolver:
                  self.delay, nat.modes(*modes), 0, self.chance_level, _stream(self.device))
 
     def _sweep_begin(self, bufs, p, evaluate, src_own, src_opp):
+        defer_w = 0.0
+        if not evaluate and self.algo != nat.ALGO_CFR_PLUS:  # this sweep walks the opponent's rows: its pending average goes in
+            defer_w, self._pending[1 - p] = self._pending[1 - p], 0.0
         nat.call("prl_board_sweep", C.byref(self.g), p, int(evaluate), src_own, src_opp, self._trunk_reach_row(bufs, 1 - p),
-                 self.iter_counter, self.delay, _stream(self.device))
+                 self.iter_counter, self.delay, self.algo, defer_w, 0, _stream(self.device))
+
+    def flush_average(self):
+        """Vanilla / Linear CFR: adds the average-strategy contributions that are still pending (a light P1-only sweep per seat)"""
+        with torch.cuda.device(self.device):
+            for q in (0, 1):
+                if self._pending[q] != 0.0:
+                    nat.call("prl_board_sweep", C.byref(self.g), 1 - q, 0, 0, 0, self._trunk_reach_row(self.bufs, q),
+                             self.iter_counter, self.delay, self.algo, self._pending[q], 1, _stream(self.device))
+                    self._pending[q] = 0.0
 
     def _sweep_end(self, bufs, p, evaluate):
         """level-kernel trunk path: cross-rank sum, then the chance node's rows into the level kernels' workspace"""
@@ -282,6 +299,10 @@ class BoardCFRSolver:
     def _update_end(self, p):
         """second half: cross-rank sum, chance node row, trunk regrets / matching / averaging, trunk reach of p"""
         cl = self.chance_level
+        if self.algo != nat.ALGO_CFR_PLUS:  # VanillaCFR.py:56-59 / LinearCFR.py:55-58: weight of this update's strategy in the sums
+            if not self.fused_trunk:
+                raise RuntimeError("Vanilla / Linear CFR on the board engine need the fused trunk (unset PRL_TRUNK=levels)")
+            self._pending[p] = float(self.iter_counter + 1) if self.algo == nat.ALGO_LINEAR else 1.0
         if self.fused_trunk:
             self._reduce(self.w_total[:1])
             self._trunk(self.bufs, self.modes, False, p)
@@ -301,6 +322,7 @@ class BoardCFRSolver:
             self.iter_counter = 0
             for t in (self.regret, self.avg, self.bufs.regret, self.bufs.strat, self.bufs.avg):
                 t.zero_()
+            self._pending = [0.0, 0.0]
             self.modes = [nat.STRAT_UNIFORM64, nat.STRAT_UNIFORM64]
             self._reach_trunk(self.bufs, 3, -1, -1, self.modes)
 
@@ -338,11 +360,14 @@ class BoardCFRSolver:
 
     def exploitability_average(self):
         if self.iter_counter <= self.delay:
-            raise RuntimeError("CFR+ has no average strategy before iteration delay+1 (CFRPlus.py:33-35)")
+            raise RuntimeError("no average strategy before iteration delay+1 (CFRPlus.py:33-35)")
         with torch.cuda.device(self.device):
             if self._eval_bufs is None:
                 self._eval_bufs = TreeBuffers(self.trunk, share=self.bufs)
-            if self.iter_counter == self.delay + 1:  # avg == copy of the current strategy (CFRPlus.py:83-84)
+            if self.algo != nat.ALGO_CFR_PLUS:  # normalised reach-weighted sums (LinearCFR.py:64-71, VanillaCFR.py:65-72)
+                self.flush_average()
+                modes, src = [nat.STRAT_AVG_SUM, nat.STRAT_AVG_SUM], SRC_AVG_SUM
+            elif self.iter_counter == self.delay + 1:  # avg == copy of the current strategy (CFRPlus.py:83-84)
                 modes, src = [nat.STRAT_F32, nat.STRAT_F32], SRC_REGRET
             else:
                 modes, src = [nat.STRAT_AVG_F32, nat.STRAT_AVG_F32], SRC_AVG
@@ -354,6 +379,7 @@ class BoardCFRSolver:
         """(regret, avg) as natural-order float32 [ft.n_slots, ld] tensors in the slot order of the flat tree `ft` built over
         THIS rank's boards (for agents, exports and parity tests on small instances)."""
         assert ft.board_spec.boards.shape[0] == self.n_boards
+        self.flush_average()
         st = ft.board_subtree()
         out = []
         dev = self.device
@@ -377,6 +403,7 @@ class BoardCFRSolver:
 
     def load_natural_tables(self, ft, regret, avg):
         """inverse of natural_tables (teacher forcing in the parity tests, checkpoints written by the level engine)"""
+        self._pending = [0.0, 0.0]  # the given average is complete
         st = ft.board_subtree()
         dev = self.device
         src, dst = [], []
@@ -413,6 +440,7 @@ class BoardCFRSolver:
             self._reach_trunk(self.bufs, 3, -1, -1, self.modes)
 
     def state_dict(self):
+        self.flush_average()
         return {"engine": "board", "algo": self.algo_name, "delay": self.delay, "iter_counter": self.iter_counter,
                 "modes": list(self.modes), "rank": self.rank, "world": self.world, "n_boards": self.n_boards,
                 "n_boards_total": self.n_boards_total, "regret": self.regret.cpu(), "avg": self.avg.cpu(),
@@ -426,6 +454,7 @@ class BoardCFRSolver:
         if tuple(state["regret"].shape) != tuple(self.regret.shape):
             raise ValueError("checkpoint table shape %s != %s" % (tuple(state["regret"].shape), tuple(self.regret.shape)))
         self.iter_counter, self.modes = int(state["iter_counter"]), list(state["modes"])
+        self._pending = [0.0, 0.0]  # state_dict() flushes before it exports
         self.regret.copy_(state["regret"])
         self.avg.copy_(state["avg"])
         self.bufs.regret.copy_(state["trunk_regret"])

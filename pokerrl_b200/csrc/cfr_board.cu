@@ -163,7 +163,10 @@ struct SweepArgs {
     const float* trunk_reach_opp;  // natural order row of the opponent's reach at the chance node
     int iter, delay;
     float m_old, m_new;            // CFRPlus.py:68-73
-    int src_own, src_opp;          // evaluation: 0 = regret matching of `regret`, 1 = `avg` rows as they are
+    int src_own, src_opp;          // evaluation: 0 = regret matching of `regret`, 1 = `avg` rows as they are (CFR+ average),
+                                   // 2 = `avg` rows normalised (reach-weighted sums of Vanilla / Linear CFR, LinearCFR.py:64-71)
+    float rw;                      // weight of the instantaneous regret: 1, Linear CFR iter + 1 (LinearCFR.py:27-28)
+    float defer_w;                 // DEFER: weight of the opponent's pending average-strategy contribution (0: none)
     double fx_scale;               // 2^frac_bits
     float sc[16];                  // terminal n: K * pot / 2, negated where the seat of this sweep is the folder
 };
@@ -232,8 +235,14 @@ __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 // EVAL = true: values and best-response values of seat P under the strategies selected by src_own / src_opp.
 // Table rows of board j: [j][14][1088] floats, rows ShapeFHP::row_of(child); everything a unit touches is contiguous.
 // =====================================================================================================================
-template <class SH, int P, bool EVAL>
+// DEFER (Vanilla / Linear CFR, update form): regrets are not clipped, and the average is the reach-weighted SUM of
+// strategies (VanillaCFR.py:54-60, LinearCFR.py:53-59) with the seat's reach under its NEW strategy - which includes its
+// new trunk reach, known only after this seat's trunk update.  The contribution of seat q's update is therefore added
+// during the NEXT sweep that walks q's rows anyway: P1 of the other seat's sweep computes exactly q's strategy and reach
+// at every node (defer_w = its weight).  P1ONLY: nothing but that (flush before an evaluation of the average strategy).
+template <class SH, int P, bool EVAL, bool DEFER = false, bool P1ONLY = false>
 __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArgs a) {
+    static_assert(!(EVAL && DEFER) && (!P1ONLY || DEFER), "variants");
     extern __shared__ __align__(128) unsigned char smem[];
     float* S = reinterpret_cast<float*>(smem + kSOff);
     float* Er = reinterpret_cast<float*>(smem + kErOff);
@@ -259,9 +268,11 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
     constexpr size_t kBoardFloats = (size_t)ROWS * kLdb;
     const unsigned char* blob_g = reinterpret_cast<const unsigned char*>(G.tables);
     // tables the two seats' strategies come from (evaluation: regret matching of `regret` or the rows of `avg`)
-    const float* tab_opp = (EVAL && a.src_opp == 1) ? G.avg : G.regret;
-    const float* tab_own = (EVAL && a.src_own == 1) ? G.avg : G.regret;
-    const bool do_avg = !EVAL && a.iter >= a.delay;
+    const float* tab_opp = (EVAL && a.src_opp >= 1) ? G.avg : G.regret;
+    const float* tab_own = (EVAL && a.src_own >= 1) ? G.avg : G.regret;
+    const int asis_opp = (EVAL && a.src_opp == 1) ? 1 : 0, asis_own = (EVAL && a.src_own == 1) ? 1 : 0;
+    const bool do_avg = !EVAL && !DEFER && a.iter >= a.delay;
+    const bool defer_now = DEFER && a.defer_w != 0.0f;
     const bool read_avg = do_avg && a.m_old != 0.0f;
 
     // private chance-sum accumulators of this CTA (global, L2-resident): [2][kRange] int64
@@ -282,12 +293,15 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         bulk_prefetch_l2(tab_opp + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb, NOPP * kLdb * 4);
         bulk_prefetch_l2(tab_own + (size_t)jj * kBoardFloats + (size_t)OWN0 * kLdb, NOWN * kLdb * 4);
         if (read_avg) bulk_prefetch_l2(G.avg + (size_t)jj * kBoardFloats + (size_t)OWN0 * kLdb, NOWN * kLdb * 4);
+        if (defer_now) bulk_prefetch_l2(G.avg + (size_t)jj * kBoardFloats + (size_t)OPP0 * kLdb, NOPP * kLdb * 4);
     };
     if (tid == 0 && j < nb) {  // first board's tables
         mbar_expect_tx(&bars[0], kBlobA);
         bulk_g2s(smem + kBlobOff, blob_g + (size_t)j * kBlobBytes, kBlobA, &bars[0]);
-        mbar_expect_tx(&bars[2], kRowIdxBytes);
-        bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)j * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
+        if (!P1ONLY) {
+            mbar_expect_tx(&bars[2], kRowIdxBytes);
+            bulk_g2s(smem + kRowIdxOff, blob_g + (size_t)j * kBlobBytes + kBlobA, kRowIdxBytes, &bars[2]);
+        }
         prefetch_rows(j);
     }
 
@@ -343,9 +357,19 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                             float gg[A], s[A];
 #pragma unroll
                             for (int c = 0; c < A; ++c) gg[c] = gk[SH::row_of(fc + c) - OPP0];
-                            node_strategy<A>(gg, EVAL ? a.src_opp : 0, s);
+                            node_strategy<A>(gg, asis_opp, s);
 #pragma unroll
                             for (int c = 0; c < A; ++c) x[fc + c] = x[n] * s[c];
+                            if constexpr (DEFER) {
+                                if (defer_now) {  // avg_strat_sum += strategy * reach * weight (VanillaCFR.py:56-59, LinearCFR.py:55-58)
+                                    float* arow = G.avg + (size_t)j * kBoardFloats + i;
+#pragma unroll
+                                    for (int c = 0; c < A; ++c) {
+                                        float* ap = arow + (size_t)SH::row_of(fc + c) * kLdb;
+                                        st_stream(ap, __fadd_rn(ld_stream(ap), __fmul_rn(x[fc + c], a.defer_w)));
+                                    }
+                                }
+                            }
                         } else {
 #pragma unroll
                             for (int c = 0; c < A; ++c) x[fc + c] = x[n];
@@ -376,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             for (int k = 0; k < kPerThread; ++k) p1_hand(k, p1_g[k], p1_x0[k]);
         }
         __syncthreads();  // B1: S complete
+        if constexpr (!P1ONLY) {
 
         // ------------------------------------------------------------------------------------------ P2a: card rows
         // quad (live card lc, lane q): entries [12 q, 12 q + 12) of the card's row in strength order.  Showdown vectors:
@@ -678,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                         float g[A], s[A];
 #pragma unroll
                         for (int c = 0; c < A; ++c) g[c] = gown[r0 + c];
-                        node_strategy<A>(g, EVAL ? a.src_own : 0, s);
+                        node_strategy<A>(g, asis_own, s);
                         float v = s[0] * e[fc];
 #pragma unroll
                         for (int c = 1; c < A; ++c) v += s[c] * e[fc + c];
@@ -690,8 +715,11 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                             br[n] = b;
                         } else {
 #pragma unroll
-                            for (int c = 0; c < A; ++c) g[c] = fmaxf((e[fc + c] - v) + g[c], 0.0f);  // CFRPlus.py:37-41
-                            node_strategy<A>(g, 0, s);
+                            for (int c = 0; c < A; ++c) {
+                                if constexpr (DEFER) g[c] = __fadd_rn(__fmul_rn(a.rw, e[fc + c] - v), g[c]);  // VanillaCFR.py:26-27, LinearCFR.py:27-28
+                                else g[c] = fmaxf((e[fc + c] - v) + g[c], 0.0f);                          // CFRPlus.py:37-41
+                            }
+                            if constexpr (!DEFER) node_strategy<A>(g, 0, s);
 #pragma unroll
                             for (int c = 0; c < A; ++c) st_stream(reg_rows + (size_t)(r0 + c) * kLdb + i, g[c]);
                             if (do_avg) {  // CFRPlus.py:65-87 (not reach-weighted)
@@ -720,6 +748,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         p3_load(2, gA, aA);
         if (p3_pos(1) < kLive) p3_hand(1, gB, aB);
         if (p3_pos(2) < kLive) p3_hand(2, gA, aA);
+        }  // !P1ONLY
         // next unit's P1 inputs: requested before the barrier below, consumed after it (the other table buffer is long there)
         if (jn < nb) {
             mbar_wait(&bars[buf ^ 1], ((it + 1) >> 1) & 1);
@@ -856,10 +885,15 @@ __global__ void board_permute_kernel(const unsigned char* __restrict__ tables, i
 // =====================================================================================================================
 constexpr int kTrunkThreads = 1024;
 
-__device__ __forceinline__ float trunk_sigma(const prl_trunk_t& t, int src, int slot, int A, int h) {
+__device__ __forceinline__ float trunk_sigma(const prl_trunk_t& t, int src, int fs, int c, int A, int h) {
     if (src == PRL_STRAT_UNIFORM64) return 1.0f / (float)A;
+    if (src == PRL_STRAT_AVG_SUM) {  // reach-weighted sums, normalised on the fly (LinearCFR.py:64-71, VanillaCFR.py:65-72)
+        float tot = 0.0f;
+        for (int k = 0; k < A; ++k) tot += t.avg[(size_t)(fs + k) * t.ld + h];
+        return (tot == 0.0f) ? 1.0f / (float)A : t.avg[(size_t)(fs + c) * t.ld + h] / tot;
+    }
     const float* tab = (src == PRL_STRAT_F32) ? t.strat : t.avg;
-    return tab[(size_t)slot * t.ld + h];
+    return tab[(size_t)(fs + c) * t.ld + h];
 }
 
 // peers != NULL: the cross-GPU sum is done HERE - every rank's fixed-point vector sits in symmetric (peer-mapped) memory and
@@ -870,7 +904,8 @@ __global__ void __launch_bounds__(kTrunkThreads) trunk_kernel(const prl_trunk_t 
                                                               const long long* const* __restrict__ peers, int n_peers,
                                                               long long peer_offset, long long* __restrict__ w_scratch,
                                                               const int16_t* __restrict__ sym_perm, int n_sym, double inv_scale,
-                                                              int p_upd, int iter, int delay, float m_old, float m_new, float* out_expl) {
+                                                              int p_upd, int iter, int delay, float m_old, float m_new, int algo,
+                                                              float rw, float* out_expl) {
     __shared__ float ro[kRange + 2];
     __shared__ float cs[64];
     __shared__ float red[32];
@@ -955,21 +990,22 @@ __global__ void __launch_bounds__(kTrunkThreads) trunk_kernel(const prl_trunk_t 
                     if (EVAL)
                         for (int c = 0; c < A; ++c) b += br_p[(size_t)(fc + c) * ld + h];
                 } else {
-                    for (int c = 0; c < A; ++c) v += trunk_sigma(t, t.mode[p], fs + c, A, h) * ev_p[(size_t)(fc + c) * ld + h];
+                    for (int c = 0; c < A; ++c) v += trunk_sigma(t, t.mode[p], fs, c, A, h) * ev_p[(size_t)(fc + c) * ld + h];
                     if (EVAL) {
                         b = br_p[(size_t)fc * ld + h];
                         for (int c = 1; c < A; ++c) b = fmaxf(b, br_p[(size_t)(fc + c) * ld + h]);
-                    } else {  // CFRPlus.py:37-63
+                    } else {  // CFRPlus.py:37-63; VanillaCFR.py:26-52 / LinearCFR.py:27-51: weighted, unclipped, matching on the positive part
                         float ssum = 0.0f;
                         for (int c = 0; c < A; ++c) {
                             float* rg = t.regret + (size_t)(fs + c) * ld + h;
-                            const float r = fmaxf((ev_p[(size_t)(fc + c) * ld + h] - v) + *rg, 0.0f);
+                            const float d = ev_p[(size_t)(fc + c) * ld + h] - v;
+                            const float r = (algo == PRL_ALGO_CFR_PLUS) ? fmaxf(d + *rg, 0.0f) : __fadd_rn(__fmul_rn(rw, d), *rg);
                             *rg = r;
-                            ssum += r;
+                            ssum += fmaxf(r, 0.0f);
                         }
                         const float inv = (ssum > 0.0f) ? 1.0f / ssum : 0.0f;
                         for (int c = 0; c < A; ++c) {
-                            const float r = t.regret[(size_t)(fs + c) * ld + h];
+                            const float r = fmaxf(t.regret[(size_t)(fs + c) * ld + h], 0.0f);
                             t.strat[(size_t)(fs + c) * ld + h] = (ssum > 0.0f) ? r * inv : 1.0f / (float)A;
                         }
                     }
@@ -994,10 +1030,9 @@ __global__ void __launch_bounds__(kTrunkThreads) trunk_kernel(const prl_trunk_t 
                     float s = 1.0f;
                     if (k == p) {
                         s = t.strat[(size_t)(fs + c) * ld + h];
-                        if (iter >= delay) {
-                            float* a = t.avg + (size_t)(fs + c) * ld + h;
-                            *a = m_old * (*a) + m_new * s;
-                        }
+                        float* a = t.avg + (size_t)(fs + c) * ld + h;
+                        if (algo != PRL_ALGO_CFR_PLUS) *a = __fadd_rn(*a, __fmul_rn(__fmul_rn(s, r), rw));  // VanillaCFR.py:56-59, LinearCFR.py:55-58
+                        else if (iter >= delay) *a = m_old * (*a) + m_new * s;
                     }
                     rp[(size_t)(fc + c) * ld + h] = s * r;
                 }
@@ -1049,9 +1084,9 @@ int default_grid() {
     return cached[dev];
 }
 
-template <int P, bool EVAL>
+template <int P, bool EVAL, bool DEFER = false, bool P1ONLY = false>
 int launch_sweep(const SweepArgs& a, int grid, cudaStream_t s) {
-    auto kern = board_sweep_kernel<ShapeFHP, P, EVAL>;
+    auto kern = board_sweep_kernel<ShapeFHP, P, EVAL, DEFER, P1ONLY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);  // per device: set every time
     if (e != cudaSuccess) return prl::check(e, "prl_board_sweep: shared memory opt-in");
     kern<<<grid, kThreads, kSmemBytes, s>>>(a);
@@ -1092,7 +1127,10 @@ extern "C" int prl_board_build_tables(const int32_t* ranks, const uint64_t* boar
 }
 
 extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int src_own, int src_opp, const float* trunk_reach_opp,
-                               int iter, int delay, prl_stream_t stream) {
+                               int iter, int delay, int algo, float defer_w, int p1_only, prl_stream_t stream) {
+    if (algo != PRL_ALGO_CFR_PLUS && algo != PRL_ALGO_VANILLA && algo != PRL_ALGO_LINEAR) return prl::fail("prl_board_sweep: bad algo");
+    const bool defer = !eval && algo != PRL_ALGO_CFR_PLUS;
+    if (p1_only && !defer) return prl::fail("prl_board_sweep: p1_only is the average flush of Vanilla / Linear CFR");
     if (!g || !shape_matches(g)) return prl::fail("prl_board_sweep: the post-deal subtree does not have the compiled shape");
     if (g->n_range != kRange || g->n_deck != kDeck) return prl::fail("prl_board_sweep: 52-card deck / 1326 hands only");
     if (!layout_matches(g)) return prl::fail("prl_board_sweep: row0 / row_m must be the board-major layout of prl_board_rows");
@@ -1112,10 +1150,16 @@ extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int s
     a.m_new = (iter > delay) ? (float)(nw / (cw + nw)) : 1.0f;
     a.src_own = src_own;
     a.src_opp = src_opp;
+    a.rw = (algo == PRL_ALGO_LINEAR) ? (float)(iter + 1) : 1.0f;
+    a.defer_w = defer ? defer_w : 0.0f;
     a.fx_scale = (double)(1ull << g->frac_bits);
     for (int n = 0; n < 16; ++n) {
         const bool folder = n < g->n_local && g->kind[n] == PRL_KIND_FOLD && g->acted_last[n] == p;
         a.sc[n] = (n < g->n_local) ? g->eq_const * g->pot[n] * 0.5f * (folder ? -1.0f : 1.0f) : 0.0f;
+    }
+    if (p1_only) {
+        const int rc1 = (p == 0) ? launch_sweep<0, false, true, true>(a, grid, s) : launch_sweep<1, false, true, true>(a, grid, s);
+        return rc1 ? rc1 : prl::check(cudaGetLastError(), "prl_board_sweep(flush)");
     }
     {   // the sums this launch produces: update -> w_total[0]; evaluation of seat p -> w_total[2p], w_total[2p + 1]
         char* base = reinterpret_cast<char*>(g->w_total) + (eval ? sizeof(long long) * 2 * p * kRange : 0);
@@ -1123,6 +1167,7 @@ extern "C" int prl_board_sweep(const prl_board_game_t* g, int p, int eval, int s
     }
     int rc;
     if (eval) rc = (p == 0) ? launch_sweep<0, true>(a, grid, s) : launch_sweep<1, true>(a, grid, s);
+    else if (defer) rc = (p == 0) ? launch_sweep<0, false, true>(a, grid, s) : launch_sweep<1, false, true>(a, grid, s);
     else rc = (p == 0) ? launch_sweep<0, false>(a, grid, s) : launch_sweep<1, false>(a, grid, s);
     if (rc) return rc;
     return prl::check(cudaGetLastError(), "prl_board_sweep");
@@ -1149,7 +1194,9 @@ extern "C" int prl_board_permute(const prl_board_game_t* g, int rows_per_board, 
 // Trunk of seat p's half-iteration (eval == 0) or of an evaluation of both seats (eval != 0) in one launch; see prl_trunk_t.
 extern "C" int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, int eval, int p, int n_sym, const int16_t* sym_perm,
                                int iter, int delay, float* out_expl, const int64_t* const* peers, int n_peers,
-                               int64_t peer_offset, int64_t* w_scratch, prl_stream_t stream) {
+                               int64_t peer_offset, int64_t* w_scratch, int algo, prl_stream_t stream) {
+    if (algo != PRL_ALGO_CFR_PLUS && algo != PRL_ALGO_VANILLA && algo != PRL_ALGO_LINEAR) return prl::fail("prl_board_trunk: bad algo");
+    const float rw = (algo == PRL_ALGO_LINEAR) ? (float)(iter + 1) : 1.0f;
     if (!g || !t || t->n_nodes < 1 || t->n_nodes > 8) return prl::fail("prl_board_trunk: 1..8 trunk nodes");
     if (t->n_range != kRange || g->n_deck != kDeck) return prl::fail("prl_board_trunk: 52-card deck / 1326 hands only");
     if (eval && !out_expl) return prl::fail("prl_board_trunk: out_expl missing");
@@ -1166,10 +1213,10 @@ extern "C" int prl_board_trunk(const prl_board_game_t* g, const prl_trunk_t* t, 
     long long* ws = reinterpret_cast<long long*>(w_scratch);
     if (eval)
         trunk_kernel<true><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, pp, n_peers, (long long)peer_offset, ws, sym_perm, n_sym,
-                                                                       inv_scale, -1, iter, delay, m_old, m_new, out_expl);
+                                                                       inv_scale, -1, iter, delay, m_old, m_new, algo, rw, out_expl);
     else
         trunk_kernel<false><<<1, kTrunkThreads, 0, (cudaStream_t)stream>>>(*t, w, pp, n_peers, (long long)peer_offset, ws, sym_perm, n_sym,
-                                                                        inv_scale, p, iter, delay, m_old, m_new, out_expl);
+                                                                        inv_scale, p, iter, delay, m_old, m_new, algo, rw, out_expl);
     prl::count_launch();
     return prl::check(cudaGetLastError(), "prl_board_trunk");
 }

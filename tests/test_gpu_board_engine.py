@@ -105,7 +105,7 @@ def test_root_rows_against_reference_anchored_golden_rows():
             row[:1326] = torch.from_numpy(reach[b]).to(s.device)
             s.t_mult.zero_()
             s.t_mult[b] = 1.0
-            nat.call("prl_board_sweep", C.byref(s.g), p, 1, 0, 0, C.c_void_p(row.data_ptr()), 0, 0,
+            nat.call("prl_board_sweep", C.byref(s.g), p, 1, 0, 0, C.c_void_p(row.data_ptr()), 0, 0, nat.ALGO_CFR_PLUS, 0.0, 0,
                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
             got = s.w_total[2 * p].cpu().numpy().astype(np.float64) / 2.0 ** s.g.frac_bits  # evaluation of seat p: arrays 2p, 2p + 1
             ref = (coef_sd * GOLD["showdown"][b] + coef_fold * GOLD["fold"][b]) * 2.0 ** -10
@@ -115,9 +115,9 @@ def test_root_rows_against_reference_anchored_golden_rows():
     print("board sweep root rows vs brute-force golden rows: worst relative error seat0 %.2e seat1 %.2e" % (worst[0], worst[1]))
 
 
-def _oracle(ft, **kw):
+def _oracle(ft, algo="CFRPlus", **kw):
     from twocard_common import oracle_tree
-    return cfr2_c.Oracle2CSolver(ft, oracle_tree(ft).board_ranks, "CFRPlus", n_threads=8, **kw)
+    return cfr2_c.Oracle2CSolver(ft, oracle_tree(ft).board_ranks, algo, n_threads=8, **kw)
 
 
 def _natural(s, ft):
@@ -184,6 +184,73 @@ def test_teacher_forced_steps_match_float64_oracle(iso):
         orc.iter_counter += 1
     print("teacher-forced relative errors (expl current, expl average, regrets, average) per half-iteration:",
           ["%.1e %.1e %.1e %.1e" % e for e in errs])
+
+
+@pytest.mark.parametrize("algo", ["LinearCFR", "VanillaCFR"])
+def test_linear_and_vanilla_cfr_teacher_forced(algo):
+    """Vanilla / Linear CFR on the board engine (unclipped weighted regrets; the reach-weighted average sums of a seat are added
+    by the NEXT sweep over its rows or by flush_average): every half-iteration from the oracle's tables, regrets, average sums
+    and the exploitability of the current / the normalised average strategy at 1e-6."""
+    spec = random_board_spec(40, 17)
+    ft = fhp_tree(spec)
+    orc = _oracle(ft, algo, lean=True)
+    s = _engine(spec, algo=algo)
+    live = _live_mask(ft, spec.boards)
+    dec = np.nonzero((ft.kind <= 1) & (ft.first_child >= 0))[0]
+    errs = []
+    for t in range(4):
+        for p in (0, 1):
+            s.load_natural_tables(ft, orc.regret, orc.avg)
+            s.set_trunk_strategy_from_regrets()
+            s.iter_counter = orc.iter_counter
+            e1 = e2 = 0.0
+            if p == 0:
+                a, b = s.exploitability_current(), orc.exploitability_current()
+                e1 = abs(a - b) / abs(b)
+                if t > 0:
+                    a, b = s.exploitability_average(), orc.exploitability_average()
+                    e2 = abs(a - b) / abs(b)
+            s._update_begin(p)
+            s._update_end(p)
+            orc.half_iteration(p)
+            reg, avg = _natural(s, ft)  # flushes seat p's pending average contribution
+            e3 = _rel(reg * live, orc.regret * live)
+            # the sums take in sigma = r+ / sum(r+) of the UPDATED regrets, which amplifies a regret error by max|r| / sum(r+)
+            # (a hand whose actions tie has regrets of round-off size and a strategy decided by it): weighted by that
+            # condition number like the CFR+ average above; the unweighted difference is printed as well
+            rp = np.maximum(orc.regret, 0.0)
+            cond = np.zeros(orc.regret.shape)
+            for n in dec[ft.kind[dec] == p]:
+                fs, A = ft.first_slot[n], ft.n_children[n]
+                cond[fs:fs + A] = np.minimum(rp[fs:fs + A].sum(axis=0) / np.abs(orc.regret).max(), 1.0)
+            scale = max(np.abs(orc.avg).max(), 1e-300)
+            e4 = float((np.abs(avg - orc.avg) * cond * live).max() / scale)
+            e5 = _rel(avg * live, orc.avg * live)
+            errs.append((e1, e2, e3, e4, e5))
+            assert max(e1, e2, e3, e4) <= TOL, (algo, t, p, e1, e2, e3, e4, e5)
+        s.iter_counter += 1
+        orc.iter_counter += 1
+    print(algo, "teacher-forced relative errors (expl current, expl average, regrets, average sums conditioned / raw) per "
+          "half-iteration:", ["%.1e %.1e %.1e %.1e %.1e" % e for e in errs])
+
+
+@pytest.mark.parametrize("algo", ["LinearCFR", "VanillaCFR"])
+def test_linear_and_vanilla_free_running_against_level_engine(algo):
+    """the deferred average of the board engine against the level engine's in-sweep average: 5 free-running iterations"""
+    from pokerrl_b200.solver import CFRSolver
+    spec = random_board_spec(32, 6)
+    ft = fhp_tree(spec)
+    s, lv = _engine(spec, algo=algo), CFRSolver(ft, algo)
+    out = []
+    for t in range(5):
+        s.iteration(1)
+        lv.iteration(1)
+        a, c = s.exploitability_current(), lv.exploitability_current()
+        x, z = s.exploitability_average(), lv.exploitability_average()
+        out.append((abs(a - c) / abs(c), abs(x - z) / abs(z)))
+        assert max(out[-1]) <= 5e-2, (algo, t, out[-1])
+    print(algo, "board engine vs level engine (current, average):", ["%.1e %.1e" % e for e in out])
+    assert out[0][0] <= 1e-5 and out[0][1] <= 1e-5  # the first iteration has no ties to amplify
 
 
 def test_free_running_trajectory_and_level_engine():
