@@ -160,3 +160,25 @@ def test_full_game_preflop_equities_against_brute_force():
     e1 = s.exploitability_average()
     print("push/fold Flop5Holdem, 3 bb: exploitability %.3f -> %.4f mbb/g after 200 CFR+ iterations" % (e0, e1))
     assert 0 <= e1 < 0.02 * e0
+
+
+def test_push_fold_game_through_the_cfr_facade():
+    """CFRPlus(game_cls=Flop5Holdem, starting_stack_sizes=[300]) - the reference's constructor - picks the level engine
+    with the dense all-in terminal and logs the reference's experiment names; series against the float64 oracle"""
+    from pokerrl_b200.cfr.CFRPlus import CFRPlus
+    from pokerrl_b200.game.games import Flop5Holdem
+    from pokerrl_b200.rl.base_cls.workers.ChiefBase import ChiefBase
+    spec = random_board_spec(40, 4)
+    chief = ChiefBase(t_prof=None)
+    cfr = CFRPlus(name="pf", chief_handle=chief, game_cls=Flop5Holdem, agent_bet_set=[1.0], starting_stack_sizes=[300], delay=0,
+                  board_spec=spec)
+    c = o2.Oracle2CFR(oracle_tree(fhp_tree(spec, stack=300)), "CFRPlus", ev_normalizer=Flop5Holdem.EV_NORMALIZER)
+    ref = [c.exploitability_current()]
+    for _ in range(2):
+        cfr.iteration()
+        c.iteration()
+        ref.append(c.exploitability_current())
+    got = [v for _, v in chief.get_experiments()["pf_Curr_S300_total_CFRp_delay0"]["Evaluation/MBB_per_G"]]
+    errs = [abs(a - b) / abs(b) for a, b in zip(got, ref)]
+    print("push/fold through the facade: current-strategy exploitability", got, "relative errors", ["%.1e" % e for e in errs])
+    assert len(got) == 3 and max(errs[:2]) <= TOL and errs[2] <= 1e-4
