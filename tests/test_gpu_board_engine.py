@@ -218,11 +218,19 @@ def test_linear_and_vanilla_cfr_teacher_forced(algo):
             # the sums take in sigma = r+ / sum(r+) of the UPDATED regrets, which amplifies a regret error by max|r| / sum(r+)
             # (a hand whose actions tie has regrets of round-off size and a strategy decided by it): weighted by that
             # condition number like the CFR+ average above; the unweighted difference is printed as well
+            # ... and the seat's reach at a node is the product of its strategies above it (trunk included), so a node's
+            # weight is the product of the condition numbers along its path
             rp = np.maximum(orc.regret, 0.0)
             cond = np.zeros(orc.regret.shape)
-            for n in dec[ft.kind[dec] == p]:
+            node_cond = {}
+            for n in dec[ft.kind[dec] == p]:  # ascending ids: ancestors first
                 fs, A = ft.first_slot[n], ft.n_children[n]
-                cond[fs:fs + A] = np.minimum(rp[fs:fs + A].sum(axis=0) / np.abs(orc.regret).max(), 1.0)
+                c = np.minimum(rp[fs:fs + A].sum(axis=0) / np.abs(orc.regret).max(), 1.0)
+                a = ft.parent[n]
+                while a >= 0 and a not in node_cond:
+                    a = ft.parent[a]
+                node_cond[n] = c * (node_cond[a] if a >= 0 else 1.0)
+                cond[fs:fs + A] = node_cond[n]
             scale = max(np.abs(orc.avg).max(), 1e-300)
             e4 = float((np.abs(avg - orc.avg) * cond * live).max() / scale)
             e5 = _rel(avg * live, orc.avg * live)

@@ -1,8 +1,10 @@
-"""GPU parity of the two-card (Hold'em family) sweeps against the float64 oracle (oracle/cfr2_numpy.py).
+"""GPU parity of the two-card (Hold'em family) LEVEL-engine sweeps against the float64 oracle (oracle/cfr2_numpy.py, whose
+terminal rows are pinned on the reference's hand strengths, tests/test_oracle_twocard_rows.py).
 
-Tolerance: float32 device arithmetic vs float64 oracle - node vectors within 2e-5 of the largest magnitude of the
-compared array, exploitability within 1e-5 relative (BASELINE.json's 1e-6 is stated against the reference's own
-float32 path, which does not exist for these games)."""
+Tolerances (achieved errors are printed with -s; measured on B200: reach 2e-8, values 1.6e-7, regrets over four free-running
+iterations <= 5.4e-7, exploitability <= 3e-7): 1e-6 of the largest magnitude of the compared array / relative for
+exploitability - BASELINE.json's bar - wherever the inputs are identical (uniform profile, first iterations); free-running
+trajectories of several iterations get 2e-6 .. 1e-5 (float32 round-off decides ties in regret matching, SURVEY headline 5)."""
 import numpy as np
 import pytest
 
@@ -17,12 +19,19 @@ pytestmark = pytest.mark.gpu
 ACHIEVED = {}
 
 
-def _close(name, mine, ref, tol=2e-5):
+def _close(name, mine, ref, tol=1e-6):
     scale = np.abs(ref).max()
     err = np.abs(mine - ref).max()
     ACHIEVED[name] = max(ACHIEVED.get(name, 0.0), float(err / scale))
     print("level engine vs float64 oracle: %-14s relative error %.2e (tolerance %.0e)" % (name, err / scale, tol))
     assert err <= tol * scale, (name, err, scale)
+
+
+def _expl_close(name, a, b, tol=1e-6):
+    err = abs(a - b) / abs(b)
+    ACHIEVED[name] = max(ACHIEVED.get(name, 0.0), float(err))
+    print("level engine vs float64 oracle: %-14s relative error %.2e (tolerance %.0e)" % (name, err, tol))
+    assert err <= tol, (name, a, b)
 
 
 def _node_vec(s_t, ft):  # torch [2, N, ld] -> [N, 2, R]
@@ -41,7 +50,7 @@ def test_uniform_profile_values_random_boards():
     _close("ev", _node_vec(s.bufs.ev, ft), orc.ev)
     _close("ev_br", _node_vec(s.bufs.ev_br, ft), orc.ev_br)
     ref_m = float(sum(expl) / 2 * ft.game_cls.EV_NORMALIZER)
-    assert abs(m - ref_m) <= 1e-5 * abs(ref_m), (m, ref_m)
+    _expl_close("expl uniform", m, ref_m, tol=1e-5)
     # zero-sum check of the reference (ValueFiller.py:98) at the root
     assert abs((orc.ev[0] * orc.reach[0]).sum()) < 1e-6 * np.abs(orc.ev[0]).max()
 
@@ -59,11 +68,11 @@ def test_cfr_iterations_match_oracle(algo):
         ref = np.zeros_like(reg)
         for n in c.t.decision_nodes():
             ref[ft.first_slot[n]:ft.first_slot[n] + ft.n_children[n]] = c.regret[n].T
-        _close("regret it%d" % t, reg, ref, tol=5e-5)
+        _close("regret it%d" % t, reg, ref, tol=1e-6 if t < 2 else 2e-6)
         a, b = s.exploitability_current(), c.exploitability_current()
-        assert abs(a - b) <= 2e-5 * abs(b), (t, a, b)
+        _expl_close("expl cur it%d" % t, a, b, tol=2e-5)
         a, b = s.exploitability_average(), c.exploitability_average()
-        assert abs(a - b) <= 2e-5 * abs(b), (t, a, b)
+        _expl_close("expl avg it%d" % t, a, b, tol=2e-5)
 
 
 def test_suit_isomorphism_equals_full_enumeration():
@@ -78,16 +87,18 @@ def test_suit_isomorphism_equals_full_enumeration():
     orc = o2.Oracle2CFR(oracle_tree(full), "CFRPlus", ev_normalizer=full.game_cls.EV_NORMALIZER)
     for t in range(3):
         a, b, c = s_full.exploitability_current(), s_iso.exploitability_current(), orc.exploitability_current()
-        assert abs(a - c) <= 2e-5 * abs(c) and abs(b - c) <= 2e-5 * abs(c), (t, a, b, c)
+        _expl_close("expl full-enum it%d" % t, a, c, tol=2e-5)
+        _expl_close("expl iso it%d" % t, b, c, tol=2e-5)
         # trunk (pre-deal) regrets agree between the two GPU trees and with the oracle
         ra = s_full.bufs.regret[:4, :full.R].cpu().numpy()
         rb = s_iso.bufs.regret[:4, :iso.R].cpu().numpy()
-        _close("trunk regret", rb, ra.astype(np.float64), tol=5e-5) if t else None
+        _close("trunk regret", rb, ra.astype(np.float64), tol=5e-6) if t else None
         s_full.iteration(1)
         s_iso.iteration(1)
         orc.iteration()
     a, b, c = s_full.exploitability_average(), s_iso.exploitability_average(), orc.exploitability_average()
-    assert abs(a - c) <= 2e-5 * abs(c) and abs(b - c) <= 2e-5 * abs(c), (a, b, c)
+    _expl_close("expl avg full-enum", a, c, tol=2e-5)
+    _expl_close("expl avg iso", b, c, tol=2e-5)
 
 
 def test_sharded_schedule_single_rank_equals_plain_solver():
@@ -129,15 +140,15 @@ def test_multi_street_subgame_matches_oracle():
     _close("ev", _node_vec(s.bufs.ev, ft), orc.ev)
     _close("ev_br", _node_vec(s.bufs.ev_br, ft), orc.ev_br)
     ref_m = float(sum(expl) / 2 * ft.game_cls.EV_NORMALIZER)
-    assert abs(m - ref_m) <= 1e-5 * abs(ref_m)
+    _expl_close("expl uniform (multi-street)", m, ref_m, tol=1e-5)
     c = o2.Oracle2CFR(orc, "LinearCFR", ev_normalizer=ft.game_cls.EV_NORMALIZER)
     for t in range(3):
         s.iteration(1)
         c.iteration()
         a, b = s.exploitability_current(), c.exploitability_current()
-        assert abs(a - b) <= 5e-5 * abs(b), (t, a, b)
+        _expl_close("expl multi-street it%d" % t, a, b, tol=5e-5)
         a, b = s.exploitability_average(), c.exploitability_average()
-        assert abs(a - b) <= 5e-5 * abs(b), (t, a, b)
+        _expl_close("expl multi-street it%d" % t, a, b, tol=5e-5)
 
 
 @pytest.mark.parametrize("algo", ["CFRPlus", "LinearCFR"])
@@ -159,5 +170,6 @@ def test_kernel_variants_agree(algo, monkeypatch):
         if ref is None:
             ref = got
         else:
-            _close("regret %s" % env, got[0], ref[0], tol=1e-5)
-            assert abs(got[1] - ref[1]) <= 1e-5 * abs(ref[1]) and abs(got[2] - ref[2]) <= 1e-5 * abs(ref[2]), (env, got[1:], ref[1:])
+            _close("regret %s" % env, got[0], ref[0], tol=2e-6)
+            _expl_close("expl cur %s" % env, got[1], ref[1], tol=1e-5)
+            _expl_close("expl avg %s" % env, got[2], ref[2], tol=1e-5)

@@ -20,8 +20,9 @@ g = games.Flop5Holdem
 args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[20000, 20000], bet_sizes_list_as_frac_of_pot=[1.0])
 full = BoardSpec.full_game(g.RULES)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 999
+algo = sys.argv[2] if len(sys.argv) > 2 else "CFRPlus"
 spec = BoardSpec(full.boards[:n], full.board_prob[:n], full.board_mult[:n], full.sym_perm, "first %d" % n)
-s = BoardCFRSolver(g, args, spec, device="cuda:%d" % local, rank=rank, world=world)
+s = BoardCFRSolver(g, args, spec, algo=algo, device="cuda:%d" % local, rank=rank, world=world)
 trace = []
 for _ in range(6):
     s.iteration(1)
@@ -29,7 +30,7 @@ for _ in range(6):
 chk = [float(s.bufs.regret.double().sum()), float(s.bufs.avg.double().sum())]
 single = single_chk = None
 if rank == 0:
-    one = BoardCFRSolver(g, args, spec, device="cuda:0")
+    one = BoardCFRSolver(g, args, spec, algo=algo, device="cuda:0")
     single = []
     for _ in range(6):
         one.iteration(1)
