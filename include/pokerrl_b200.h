@@ -116,12 +116,13 @@ typedef struct {
                                     terminals in `order`); lets fold and showdown rows be launched as separate kernels */
     /* two-card games, all-in showdowns before the board is complete (PRL_KIND_SHOWDOWN_ALLIN; the one-card analogue is
        ValueFiller.py:160-175): they come LAST among the terminals of a level in `order`; their values are the dense product
-       of the public state's equity matrix with the opponent's reach row (prl_allin_values, tensor cores).  Only all-in
-       nodes that see the ROOT's board are supported (one matrix). */
+       of the public board's equity matrix with the opponent's reach row (prl_allin_values, tensor cores); one matrix per
+       public board such a terminal occurs on. */
     const int64_t* level_nallin; /* HOST int64[n_levels] or NULL (= no such terminals) */
     const int32_t* allin_nodes;  /* HOST int32[sum of level_nallin]: their node ids, ascending (= by level) */
     const float* allin_pot;      /* HOST float[same]: pot of each */
-    const void* allin_tiles;     /* DEVICE: equity matrix as bf16 operand tiles (prl_allin_equity_finish) */
+    const void* const* allin_tiles; /* HOST array [same] of DEVICE pointers: the equity matrix of each node's public board as bf16
+                                       operand tiles (prl_allin_equity_finish); nodes on the same board share a pointer */
     float* allin_partial;        /* DEVICE scratch, prl_allin_partial_bytes(n_range) bytes */
 } prl_tree_t;
 

@@ -89,7 +89,7 @@ class Oracle2Tree:
         self.ev_br = np.zeros((self.N, 2, R))
         self.strategy = [None] * self.N
         self._sign = {}
-        self.allin_equity = None  # float64 [R, R], see allin_equity_matrix()
+        self.allin_equity = None  # float64 [R, R] (or {board id: matrix}), see allin_equity_matrix()
 
     def decision_nodes(self):
         ft = self.ft
@@ -145,7 +145,8 @@ class Oracle2Tree:
                         # chance node's children would be (ValueFiller.py:160-175 is the one-card analogue)
                         if self.allin_equity is None:
                             raise NotImplementedError("all-in showdown before the board is complete: set allin_equity")
-                        eq[p] = self.allin_equity @ ro
+                        E = self.allin_equity[int(b)] if isinstance(self.allin_equity, dict) else self.allin_equity
+                        eq[p] = E @ ro
                 eq *= self.K
                 if b >= 0:
                     eq[:, self.board_blocked[b]] = 0.0

@@ -18,16 +18,20 @@ def _stream(dev):
 
 
 class AllinEquity:
-    def __init__(self, rules, spec, device=None, ranks=None, chunk=16384):
-        """spec: holdem_boards.BoardSpec (boards, board_prob, board_mult, sym_perm); ranks: optional DEVICE int32
-        [n_boards, R] hand strengths of spec.boards (else computed here by prl_hand_rank_boards)."""
+    def __init__(self, rules, spec=None, device=None, ranks=None, chunk=16384, boards=None, weights=None, sym_perm=None):
+        """spec: holdem_boards.BoardSpec (boards, board_prob, board_mult, sym_perm) - or boards int8 [n, 5], weights
+        float64 [n] (deal probability x weight in the parent's sum) and sym_perm given directly; ranks: optional DEVICE
+        int32 [n_boards, R] hand strengths of the boards (else computed here by prl_hand_rank_boards)."""
         from pokerrl_b200.hand_eval import hand_rank_all_hands_on_given_boards
         from pokerrl_b200.solver import _require_cuda
         self.device = dev = _require_cuda(device)
         self.R = R = rules.RANGE_SIZE
         lut = rules.get_lut_holder()
-        boards = np.ascontiguousarray(spec.boards, np.int8)
-        w = (np.asarray(spec.board_prob, np.float64) * np.asarray(spec.board_mult, np.float64))
+        if spec is not None:
+            boards, sym_perm = spec.boards, spec.sym_perm
+            weights = np.asarray(spec.board_prob, np.float64) * np.asarray(spec.board_mult, np.float64)
+        boards = np.ascontiguousarray(boards, np.int8)
+        w = np.ascontiguousarray(weights, np.float64)
         with torch.cuda.device(dev):
             self.hand_cards = torch.from_numpy(np.ascontiguousarray(lut.LUT_IDX_2_HOLE_CARDS, np.int8)).to(dev)
             ec = torch.zeros(R, R, dtype=torch.float64, device=dev)
@@ -38,7 +42,7 @@ class AllinEquity:
                 n = int(rk.shape[0])
                 nat.call("prl_allin_equity_accumulate", C.c_void_p(rk.data_ptr()), C.c_void_p(wt[i:i + n].data_ptr()), n, R,
                          C.c_void_p(ec.data_ptr()), _stream(dev))
-            sp = spec.sym_perm
+            sp = sym_perm
             self.sym = torch.from_numpy(np.ascontiguousarray(sp, np.int16)).to(dev) if sp is not None else None
             self.tiles = torch.zeros(int(nat.lib().prl_allin_tiles_bytes(R)), dtype=torch.uint8, device=dev)
             self.partial = torch.zeros(int(nat.lib().prl_allin_partial_bytes(R)) // 4, dtype=torch.float32, device=dev)

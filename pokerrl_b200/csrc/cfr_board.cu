@@ -67,6 +67,9 @@ static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move mult
 #ifndef PRL_BV_P3BAL
 #define PRL_BV_P3BAL 0       // P3: the 313 positions of the third pass spread over all twelve warps (27 lanes each)
 #endif                       // (measured: 91.0 vs 92.2 it/s)
+#ifndef PRL_BV_NEWTON
+#define PRL_BV_NEWTON 1      // regret matching: Newton step after MUFU.RCP (<= 1 ulp); 0 = the approximation as is (2^-23 relative)
+#endif
 #ifndef PRL_BV_SPLITB3
 #define PRL_BV_SPLITB3 0     // the single-warp stage between B2 and B3 spread over nine warps (one vector / fold vector each)
 #endif                       // (measured: 89.0 vs 92.2 it/s)
@@ -220,7 +223,7 @@ __device__ __forceinline__ void node_strategy(const float (&g)[A], int src, floa
     const float sm = fmaxf(sum, 1e-37f);
     float inv;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sm));
-    inv = fmaf(inv, fmaf(-sm, inv, 1.0f), inv);
+    if (PRL_BV_NEWTON) inv = fmaf(inv, fmaf(-sm, inv, 1.0f), inv);
     inv = pos ? inv : 0.0f;
     const float uni = pos ? 0.0f : 1.0f / (float)A;  // CFRPlus.py:53-58: uniform where no regret is positive
 #pragma unroll

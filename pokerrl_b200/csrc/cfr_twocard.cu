@@ -1122,30 +1122,41 @@ int value_levels2(Ctx2 c, bool with_br, bool update, int d_hi, int d_lo, int cha
     // all-in showdowns before the deal (last among the terminals of their level): their inputs - the opponent's reach rows -
     // are complete before the sweep starts, so all of them are evaluated up front by the dense tensor-core product
     if (T.level_nallin && chance_phase != 2) {
-        std::vector<const float*> xr;
-        std::vector<float*> yr, y2r;
-        std::vector<float> sc;
-        int first = 0;
+        int n_in_range = 0, first = 0;
+        for (int d = 0; d < T.n_levels; ++d) {
+            if (d >= d_lo && d <= d_hi) n_in_range += (int)T.level_nallin[d];
+        }
+        if (n_in_range > 0 && (!T.allin_tiles || !T.allin_partial || !T.allin_nodes || !T.allin_pot))
+            return prl::fail("prl(two-card): all-in terminals need allin_nodes / allin_pot / allin_tiles / allin_partial");
         const size_t N = (size_t)T.n_nodes, ld = (size_t)T.ld;
+        std::vector<int> todo;  // indices into allin_nodes of the nodes of the level range
         for (int d = 0; d < T.n_levels; ++d) {
             const int na = (int)T.level_nallin[d];
             if (d >= d_lo && d <= d_hi)
-                for (int k = 0; k < na; ++k) {
-                    const size_t node = (size_t)T.allin_nodes[first + k];
-                    for (int p = 0; p < 2; ++p) {
-                        if (!(c.mask & (1 << p))) continue;
-                        xr.push_back(c.B.reach + ((size_t)(1 - p) * N + node) * ld);
-                        yr.push_back(c.B.ev + ((size_t)p * N + node) * ld);
-                        y2r.push_back(with_br ? c.B.ev_br + ((size_t)p * N + node) * ld : nullptr);
-                        sc.push_back(T.eq_const * T.allin_pot[first + k] * 0.5f);  // ValueFiller.py:160-175 with K, pot / 2
-                    }
-                }
+                for (int k = 0; k < na; ++k) todo.push_back(first + k);
             first += na;
         }
-        if (!xr.empty()) {
-            if (!T.allin_tiles || !T.allin_partial || !T.allin_nodes || !T.allin_pot)
-                return prl::fail("prl(two-card): all-in terminals need allin_nodes / allin_pot / allin_tiles / allin_partial");
-            if (int e = prl_allin_values(T.allin_tiles, T.n_range, xr.data(), yr.data(), y2r.data(), sc.data(), (int)xr.size(),
+        std::vector<char> done(todo.size(), 0);
+        for (size_t i0 = 0; i0 < todo.size(); ++i0) {  // one product per public board (nodes on a board share their tiles)
+            if (done[i0]) continue;
+            const void* tiles = T.allin_tiles[todo[i0]];
+            std::vector<const float*> xr;
+            std::vector<float*> yr, y2r;
+            std::vector<float> sc;
+            for (size_t i = i0; i < todo.size(); ++i) {
+                if (done[i] || T.allin_tiles[todo[i]] != tiles) continue;
+                done[i] = 1;
+                const size_t node = (size_t)T.allin_nodes[todo[i]];
+                for (int p = 0; p < 2; ++p) {
+                    if (!(c.mask & (1 << p))) continue;
+                    xr.push_back(c.B.reach + ((size_t)(1 - p) * N + node) * ld);
+                    yr.push_back(c.B.ev + ((size_t)p * N + node) * ld);
+                    y2r.push_back(with_br ? c.B.ev_br + ((size_t)p * N + node) * ld : nullptr);
+                    sc.push_back(T.eq_const * T.allin_pot[todo[i]] * 0.5f);  // ValueFiller.py:160-175 with K, pot / 2
+                }
+            }
+            if (xr.empty()) continue;
+            if (int e = prl_allin_values(tiles, T.n_range, xr.data(), yr.data(), y2r.data(), sc.data(), (int)xr.size(),
                                          T.allin_partial, (prl_stream_t)s))
                 return e;
         }

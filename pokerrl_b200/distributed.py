@@ -56,6 +56,9 @@ class ShardedCFRSolver(CFRSolver):
         ft = FlatTree(game_cls, env_args, board_spec=shard_board_spec(board_spec, rank, world) if world > 1 else board_spec,
                       root_actions=root_actions)
         self.ft = ft
+        if world > 1 and (ft.kind == nat.KIND_SHOWDOWN_ALLIN).any():
+            raise NotImplementedError("all-in showdowns before the board is complete run out over ALL boards below them: "
+                                      "not available with the boards sharded over ranks (run this tree on one GPU)")
         super().__init__(ft, algo=algo, delay=delay, device=device, avg_f64=False, persistent=False)
         # levels holding BOUNDARY chance nodes: chance nodes right below the replicated trunk (no deal above them), whose
         # children - the boards of the first chance layer - are spread over the ranks.  Deeper chance nodes are local.

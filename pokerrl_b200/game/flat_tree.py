@@ -132,9 +132,6 @@ class FlatTree:
             from pokerrl_b200.game.holdem_boards import BoardSpec, MultiStreetBoards
             n_cd = max(n.cdepth for n in self.abs_nodes)
             allin = [n for n in self.abs_nodes if n.kind == KIND_SHOWDOWN_ALLIN]
-            if allin and (any(n.cdepth != 0 for n in allin) or isinstance(board_spec, MultiStreetBoards) or root_state is not None):
-                raise NotImplementedError("two-card games: all-in showdowns are supported before the first deal of a "
-                                          "single-chance-layer game only (one equity matrix, csrc/allin_dense.cu)")
             if board_spec is None:
                 if n_cd > 1 or root_state is not None:
                     raise ValueError("sub-games / multi-street two-card trees need an explicit MultiStreetBoards spec")
@@ -342,6 +339,39 @@ class FlatTree:
         m = self.board >= 0
         # board == -1 means chance depth 0 -> global board 0 (empty)
         out[m] = bc[self.board[m]]
+        return out
+
+    def allin_completions(self):
+        """Two-card games: for every public board an all-in showdown happens on BEFORE the board is complete, the complete
+        boards it runs out over and their weights (product of deal probability x weight in the parent's sum over the missing
+        deals) - the inputs of that board's equity matrix (csrc/allin_dense.cu; one-card analogue ValueFiller.py:160-175).
+        Returns {board key: (boards int8 [n, 5], weights float64 [n], sym_perm or None)}; key = the nodes' `board` entry
+        (-1: no board yet)."""
+        from pokerrl_b200.game.holdem_boards import MultiStreetBoards
+        nodes = np.nonzero(self.kind == KIND_SHOWDOWN_ALLIN)[0]
+        out = {}
+        if nodes.size == 0:
+            return out
+        spec = self.allin_spec
+        if not isinstance(spec, MultiStreetBoards):  # one deal: every board of the spec
+            w = np.asarray(spec.board_prob, np.float64) * np.asarray(spec.board_mult, np.float64)
+            out[int(self.board[nodes[0]])] = (np.ascontiguousarray(spec.boards, np.int8), w, spec.sym_perm)
+            assert np.all(self.board[nodes] == self.board[nodes[0]])
+            return out
+        L = spec.n_layers
+        for key in np.unique(self.board[nodes]):
+            gid = max(int(key), 0)  # -1 = the root's (empty) board = global id 0
+            c = int(np.searchsorted(self.board_off, gid, side="right") - 1)  # layer of that board
+            idx, w = np.array([gid - int(self.board_off[c])], np.int64), np.ones(1)
+            for layer in range(c + 1, L + 1):  # children of the current set, layer by layer
+                par = np.asarray(spec.parents[layer], np.int64)
+                pos = {int(j): k for k, j in enumerate(idx)}
+                sel = np.nonzero(np.isin(par, idx))[0]
+                wl = np.asarray(spec.prob[layer], np.float64)[sel] * np.asarray(spec.mult[layer], np.float64)[sel]
+                w = w[[pos[int(j)] for j in par[sel]]] * wl
+                idx = sel
+            assert spec.boards[L].shape[1] == self.rules.N_TOTAL_BOARD_CARDS, "the last layer must complete the board"
+            out[int(key)] = (np.ascontiguousarray(spec.boards[L][idx], np.int8), w, None)
         return out
 
     def board_subtree(self):

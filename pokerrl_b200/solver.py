@@ -219,22 +219,26 @@ class DeviceTree:
         self.workspace_bytes = 4 * max(1, max_chance_per_level) * (chunks + 1) * self.ld * 4
 
     def _init_allin(self, ft, d, complete):
-        """All-in showdowns before the deal (PRL_KIND_SHOWDOWN_ALLIN): the equity matrix of the boards they run out over
-        (ft.allin_spec) as tensor-core operand tiles - csrc/allin_dense.cu; ValueFiller.py:160-175 is the one-card analogue."""
+        """All-in showdowns before the board is complete (PRL_KIND_SHOWDOWN_ALLIN): per public board they occur on, the equity
+        matrix of the boards it runs out over (ft.allin_completions()) as tensor-core operand tiles - csrc/allin_dense.cu;
+        ValueFiller.py:160-175 is the one-card analogue."""
         from pokerrl_b200.allin import AllinEquity
         nodes = np.nonzero(ft.kind == nat.KIND_SHOWDOWN_ALLIN)[0]
         if nodes.size == 0:
             return
-        spec = ft.allin_spec
-        ranks = self.t_board_ranks[torch.from_numpy(complete).to(self.device)] if complete.size else None
-        self.allin = AllinEquity(ft.rules, spec, device=self.device, ranks=ranks)
+        self.allin = {}
+        for key, (boards, w, sym) in ft.allin_completions().items():
+            self.allin[key] = AllinEquity(ft.rules, device=self.device, boards=boards, weights=w, sym_perm=sym)
+        first = next(iter(self.allin.values()))
         self._allin_nodes = np.ascontiguousarray(nodes, dtype=np.int32)
         self._allin_pot = np.ascontiguousarray(ft.pot[nodes], dtype=np.float32)
+        self._allin_tiles = (C.c_void_p * nodes.size)(*[self.allin[int(ft.board[n])].tiles.data_ptr() for n in nodes])
         level_of = np.searchsorted(np.asarray(ft.level_start), nodes, side="right") - 1
         self._level_nallin = np.ascontiguousarray(np.bincount(level_of, minlength=ft.n_levels), dtype=np.int64)
         d.level_nallin = self._level_nallin.ctypes.data
         d.allin_nodes, d.allin_pot = self._allin_nodes.ctypes.data, self._allin_pot.ctypes.data
-        d.allin_tiles, d.allin_partial = self.allin.tiles.data_ptr(), self.allin.partial.data_ptr()
+        d.allin_tiles = C.cast(self._allin_tiles, C.c_void_p)
+        d.allin_partial = first.partial.data_ptr()
 
     @property
     def n_nodes(self):

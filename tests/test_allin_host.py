@@ -9,7 +9,7 @@ import numpy as np
 import cfr2_numpy as o2
 from gen_golden_twocard_common import make_reach
 from pokerrl_b200.game.holdem_boards import BoardSpec
-from twocard_common import fhp_tree, oracle_allin_equity, oracle_tree, random_board_spec
+from twocard_common import fhp_tree, nl_flop_subgame, oracle_allin_equity, oracle_tree, random_board_spec
 
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "twocard_rows.npz"))
 
@@ -61,3 +61,26 @@ def test_push_fold_oracle_converges():
     assert e0 > 0 and 0 <= e1 < 0.1 * e0, (e0, e1)
     t.compute_ev()
     assert abs((t.ev[0] * t.reach[0]).sum()) < 1e-9  # zero-sum at the root (ValueFiller.py:98)
+
+
+def test_nl_subgame_all_ins_on_the_flop_and_on_the_turn():
+    """multi-street sub-game: one equity matrix per public board an all-in happens on; its completions carry the product of
+    the remaining deal probabilities; the oracle stays zero-sum at the root and CFR+ converges"""
+    ft = nl_flop_subgame()
+    an = np.nonzero(ft.kind == o2.KIND_SHOWDOWN_ALLIN)[0]
+    assert set(np.unique(ft.cdepth[an])) == {0, 1}
+    comp = ft.allin_completions()
+    assert set(comp) == set(int(b) for b in np.unique(ft.board[an]))
+    flop = comp[int(ft.board[an[ft.cdepth[an] == 0][0]])]
+    assert flop[0].shape == (12, 5) and abs(flop[1].sum() - 12 / (45 * 44)) < 1e-15  # 3 turn x 4 river cards of 45 x 44
+    for key, (boards, w, _) in comp.items():
+        if key != int(ft.board[an[ft.cdepth[an] == 0][0]]):
+            assert boards.shape == (4, 5) and abs(w.sum() - 4 / 44) < 1e-15
+    t = oracle_tree(ft)
+    cfr = o2.Oracle2CFR(t, "CFRPlus")
+    e0 = cfr.exploitability_current()
+    for _ in range(40):
+        cfr.iteration()
+    assert 0 <= cfr.exploitability_average() < 0.2 * e0
+    t.compute_ev()
+    assert abs((t.ev[0] * t.reach[0]).sum()) < 1e-9 * np.abs(t.ev[0]).max()

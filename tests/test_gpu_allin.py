@@ -11,7 +11,7 @@ import pytest
 import cfr2_numpy as o2
 from gen_golden_twocard_common import make_reach
 from pokerrl_b200.game.holdem_boards import BoardSpec
-from twocard_common import fhp_tree, oracle_tree, random_board_spec
+from twocard_common import fhp_tree, nl_flop_subgame, oracle_tree, random_board_spec
 
 pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "twocard_rows.npz"))
@@ -182,3 +182,31 @@ def test_push_fold_game_through_the_cfr_facade():
     errs = [abs(a - b) / abs(b) for a, b in zip(got, ref)]
     print("push/fold through the facade: current-strategy exploitability", got, "relative errors", ["%.1e" % e for e in errs])
     assert len(got) == 3 and max(errs[:2]) <= TOL and errs[2] <= 1e-4
+
+
+def test_nl_subgame_with_all_ins_on_two_streets_against_the_oracle():
+    """DiscretizedNLHoldem flop sub-game, 6 big blinds: all-in showdowns on the flop (one matrix over turn x river) and on
+    every turn board (one matrix each over the river) - level engine vs float64 oracle: values of the uniform profile and
+    two CFR+ iterations"""
+    from pokerrl_b200.solver import CFRSolver
+    ft = nl_flop_subgame()
+    s = CFRSolver(ft, "CFRPlus")
+    assert len(s.dtree.allin) == 4
+    orc = oracle_tree(ft)
+    c = o2.Oracle2CFR(orc, "CFRPlus", ev_normalizer=ft.game_cls.EV_NORMALIZER)
+    a, b = s.exploitability_current(), c.exploitability_current()
+    ev = s.bufs.ev.cpu().numpy()[:, :, :ft.R].transpose(1, 0, 2).astype(np.float64)
+    br = s.bufs.ev_br.cpu().numpy()[:, :, :ft.R].transpose(1, 0, 2).astype(np.float64)
+    errs = [_rel(ev, orc.ev), _rel(br, orc.ev_br), abs(a - b) / abs(b)]
+    for t in range(2):
+        s.iteration(1)
+        c.iteration()
+        reg = s.bufs.regret.cpu().numpy()[:, :ft.R].astype(np.float64)
+        ref = np.zeros_like(reg)
+        for n in c.t.decision_nodes():
+            ref[ft.first_slot[n]:ft.first_slot[n] + ft.n_children[n]] = c.regret[n].T
+        a, b = s.exploitability_current(), c.exploitability_current()
+        errs += [_rel(reg, ref), abs(a - b) / abs(b)]
+    print("NL flop sub-game with all-ins: ev %.1e ev_br %.1e expl %.1e | per iteration (regret, current): %s"
+          % (errs[0], errs[1], errs[2], " ".join("%.1e" % e for e in errs[3:])))
+    assert max(errs[:5]) <= 2e-6 and max(errs) <= 1e-4

@@ -40,7 +40,9 @@ def oracle_tree(ft):
         ranks[complete] = oracle_ranks(bc[complete])
     t = o2.Oracle2Tree(ft, lut.LUT_IDX_2_HOLE_CARDS, ranks, ft.board_prob, ft.board_mult, spec.sym_perm)
     if getattr(ft, "allin_spec", None) is not None:
-        t.allin_equity = oracle_allin_equity(ft.rules, ft.allin_spec)
+        hc = np.asarray(lut.LUT_IDX_2_HOLE_CARDS).astype(np.int64)
+        t.allin_equity = {key: o2.allin_equity_matrix(oracle_ranks(boards), w, hc, ft.rules.N_CARDS_IN_DECK, sym)
+                          for key, (boards, w, sym) in ft.allin_completions().items()}
     return t
 
 
@@ -66,3 +68,13 @@ def random_board_spec(n, seed):
     boards = np.unique(np.sort(np.stack([rng.choice(52, 5, replace=False) for _ in range(n)]), axis=1), axis=0)
     return BoardSpec(boards.astype(np.int8), np.full(len(boards), 1.0 / len(boards)), np.ones(len(boards)), None,
                      "%d random boards" % len(boards))
+
+
+def nl_flop_subgame(stack=600, cards_per_layer=((20, 25, 31), (40, 44, 49, 51)), root_board=(0, 5, 10)):
+    """DiscretizedNLHoldem (pot-size bets) rooted at a flop after SB calls / BB checks, short stacks: all-in showdowns
+    happen on the flop (turn + river to come) and on the turn (river to come); turn / river cards restricted for tests"""
+    from pokerrl_b200.game.holdem_boards import MultiStreetBoards
+    g = games.DiscretizedNLHoldem
+    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[stack, stack], bet_sizes_list_as_frac_of_pot=[1.0])
+    spec = MultiStreetBoards.subgame(g.RULES, root_board, 2, 1, cards_per_layer=[list(c) for c in cards_per_layer])
+    return FlatTree(g, args, board_spec=spec, root_actions=[1, 1])
