@@ -67,6 +67,10 @@ static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move mult
 #ifndef PRL_BV_P3BAL
 #define PRL_BV_P3BAL 0       // P3: the 313 positions of the third pass spread over all twelve warps (27 lanes each)
 #endif                       // (measured: 91.0 vs 92.2 it/s)
+#ifndef PRL_BV_ROWTOTF
+#define PRL_BV_ROWTOTF 1     // kLin: a lane's part of a card row's total summed in float (12 terms), only the quad reduction in double
+                             // (measured: +1 %, parity unchanged at <= 1.6e-7)
+#endif
 #ifndef PRL_BV_NEWTON
 #define PRL_BV_NEWTON 1      // regret matching: Newton step after MUFU.RCP (<= 1 ulp); 0 = the approximation as is (2^-23 relative)
 #endif
@@ -439,9 +443,10 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                     const float xv = Sv[idx[e]];
                     inc[e] = run;
                     run += xv;
-                    if constexpr (kLin) drun += (double)xv;
+                    if constexpr (kLin && !PRL_BV_ROWTOTF) drun += (double)xv;
                 }
                 if constexpr (kLin) {
+                    if constexpr (PRL_BV_ROWTOTF) drun = (double)run;
                     drun += __shfl_xor_sync(qmask, drun, 1, 4);
                     drun += __shfl_xor_sync(qmask, drun, 2, 4);
                     if (row_live && q == 0) rowtot[v * kRowPad + lc] = drun;

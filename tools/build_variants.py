@@ -20,6 +20,7 @@ VARIANTS = {
     "ert": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
     "splitb3_ert": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=1, ERT=1),
     "final": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
+    "rowtotf": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1, ROWTOTF=1),
     "nonewton": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1, NEWTON=0),
     "ert_p1a2": dict(RED=1, P1PIPE=2, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
     "p3bal": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, P3BAL=1),
