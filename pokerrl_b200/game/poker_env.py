@@ -34,6 +34,13 @@ class PokerEnv:
         self.N_CARDS_IN_DECK = self.rules.N_CARDS_IN_DECK
         self.IS_EVALUATING = True
         self._last = None
+        self._host = None  # host copy of (state, deck) of the table, refreshed lazily after reset / step / load_state_dict
+        # constants the evaluators read from the env (PokerEnv.py:361-368, games.py)
+        self.REWARD_SCALAR = float(self._b.cfg.reward_scalar)
+        self.EV_NORMALIZER = game_cls.EV_NORMALIZER
+        self.IS_FIXED_LIMIT_GAME = bool(game_cls.IS_FIXED_LIMIT_GAME)
+        self.bet_sizes_list_as_frac_of_pot = (sorted(env_args.bet_sizes_list_as_frac_of_pot)
+                                              if game_cls.BETTING == "discretized" else None)
 
     # ---- PokerEnv.reset (:1075-1122)
     def reset(self, deck_state_dict=None):
@@ -41,6 +48,7 @@ class PokerEnv:
         if deck_state_dict is not None:
             decks = self._deck_from_cards_state_dict(deck_state_dict)[None]
         obs, legal = self._b.reset(decks=decks)
+        self._host = None
         self._last = (obs[0].cpu().numpy().copy(), np.zeros(2, np.float64), False)
         return self._last[0], np.zeros(self.N_SEATS, np.float32), False, [False, None]
 
@@ -48,8 +56,65 @@ class PokerEnv:
     def step(self, action):
         obs, rew, done, legal = self._b.step(torch.tensor([int(action)], dtype=torch.int32))
         o, r, d = obs[0].cpu().numpy().copy(), rew[0].cpu().numpy().copy(), bool(done[0].item())
+        self._host = None
         self._last = (o, r, d)
         return o, r, d, [False, None]
+
+    def step_raise_pot_frac(self, pot_frac):
+        """PokerEnv.step_raise_pot_frac (:1124-1136) for the fractions of this table's own bet set (fixed-limit games: the one
+        raise there is); other fractions would need the continuous action space, which the device engine does not have"""
+        if self.bet_sizes_list_as_frac_of_pot is None:
+            return self.step(Poker.BET_RAISE)
+        for i, f in enumerate(self.bet_sizes_list_as_frac_of_pot):
+            if abs(float(f) - float(pot_frac)) <= 1e-9 * max(1.0, abs(float(f))):
+                return self.step(2 + i)
+        raise ValueError("pot fraction %r is not in this table's bet set %r" % (pot_frac, self.bet_sizes_list_as_frac_of_pot))
+
+    # ---- read-only views of the table the evaluators use (PokerEnv attributes / PokerPlayer fields)
+    def _state(self):
+        if self._host is None:
+            self._host = (self._b.state[:, 0].cpu().numpy(), self._b.deck[0].cpu().numpy())
+        return self._host
+
+    class _Seat:
+        def __init__(self, seat_id, stack, current_bet):
+            self.seat_id, self.stack, self.current_bet = seat_id, stack, current_bet
+
+    @property
+    def current_round(self):
+        return int(self._state()[0][_F["round"]])
+
+    @property
+    def current_player(self):
+        st = self._state()[0]
+        p = int(st[_F["cur"]])
+        return PokerEnv._Seat(p, int(st[_F["stack0"] + p]), int(st[_F["bet0"] + p]))
+
+    @property
+    def seats(self):
+        st = self._state()[0]
+        return [PokerEnv._Seat(p, int(st[_F["stack0"] + p]), int(st[_F["bet0"] + p])) for p in range(2)]
+
+    @property
+    def board(self):
+        """int8 [N_TOTAL_BOARD_CARDS, 2] (rank, suit), not-dealt tokens where nothing lies yet (PokerEnv.board)"""
+        st, d = self._state()
+        nh, nbc = self._deal_layout()
+        b = np.full(nbc, Poker.CARD_NOT_DEALT_TOKEN_1D, np.int8)
+        n_out = self.rules.n_cards_out_at(int(st[_F["round"]]))
+        b[:n_out] = d[2 * nh:2 * nh + n_out]
+        return self.lut_holder.get_2d_cards(b)
+
+    def get_all_winnable_money(self):  # main pot + side pots + the bets in front of the players (PokerEnv.py)
+        st = self._state()[0]
+        return int(st[_F["pot"]]) + int(st[_F["bet0"]]) + int(st[_F["bet1"]])
+
+    def get_hole_cards_of_player(self, p_id):
+        nh, _ = self._deal_layout()
+        return self.lut_holder.get_2d_cards(self._state()[1][p_id * nh:(p_id + 1) * nh])
+
+    def get_range_idx(self, p_id):
+        return int(self.lut_holder.get_range_idx_from_hole_cards(self.get_hole_cards_of_player(p_id)))
 
     def get_legal_actions(self):  # DiscretizedPokerEnv.get_legal_actions (:99-135) / LimitPokerEnv (:41-59)
         return [int(a) for a in np.nonzero(self._b.legal[0].cpu().numpy())[0]]
@@ -114,4 +179,5 @@ class PokerEnv:
         self._b.state[:, 0] = torch.from_numpy(raw["state"]).to(self._b.device)
         self._b.deck[0] = torch.from_numpy(raw["deck"]).to(self._b.device)
         self._b.legal[0] = torch.from_numpy(raw["legal"]).to(self._b.device)
+        self._host = None
         self._last = raw["last"]

@@ -28,6 +28,12 @@ class EnvWrapperBuilderBase:
         return args
 
 
+    def get_new_env(self, is_evaluating, stack_size=None):
+        """EnvWrapperBuilderBase.get_new_env (:96-111): a single table on the device engine"""
+        from pokerrl_b200.game.poker_env import PokerEnv
+        return PokerEnv(self.env_cls, self.args_for_stack(stack_size), lut_holder=self.lut_holder, is_evaluating=is_evaluating)
+
+
 class VanillaEnvBuilder(EnvWrapperBuilderBase):
     pass
 

@@ -34,12 +34,58 @@ class EvalAgentBase:
     def can_compute_mode(self):
         raise NotImplementedError
 
+    # ---- the agent's own table (EvalAgentBase.py:29, 128-158).  Evaluators that PLAY against the agent (LBR,
+    #      eval/lbr/LocalLBRWorker.py) keep it in step with theirs through these notifications; the table is a single-table view of
+    #      the device engine (game/poker_env.py), created on first use.
+    @property
+    def internal_env(self):
+        if getattr(self, "_internal_env", None) is None:
+            self._internal_env = self.env_bldr.get_new_env(is_evaluating=True, stack_size=self._stack_size)
+        return self._internal_env
+
+    def reset(self, deck_state_dict=None):
+        self.internal_env.reset(deck_state_dict=deck_state_dict)
+
+    def notify_of_action(self, p_id_acted, action_he_did):
+        assert self.internal_env.current_player.seat_id == p_id_acted
+        self.internal_env.step(action_he_did)
+
+    def notify_of_raise_frac_action(self, p_id_acted, frac):
+        assert self.internal_env.current_player.seat_id == p_id_acted
+        self.internal_env.step_raise_pot_frac(pot_frac=frac)
+
+    def env_state_dict(self):
+        return self.internal_env.state_dict()
+
+    def load_env_state_dict(self, state_dict):
+        self.internal_env.load_state_dict(state_dict)
+
+    def _uniform(self):
+        """one uniform random number per sampled action (tests replay recorded ones)"""
+        import numpy as np
+        return float(np.random.random())
+
+    def get_action(self, step_env=True, need_probs=False):
+        """EvalAgentBase.get_action (:52-63): sample the action of the hand the agent holds at its own table from
+        get_a_probs_for_each_hand(); optionally step the table; optionally return the whole [RANGE_SIZE, N_ACTIONS] table"""
+        import numpy as np
+        env = self.internal_env
+        probs = np.asarray(self.get_a_probs_for_each_hand())
+        row = probs[env.get_range_idx(p_id=env.current_player.seat_id)].astype(np.float64)
+        action = int(min(np.searchsorted(np.cumsum(row), self._uniform(), side="right"), row.size - 1))
+        while row[action] == 0 and action > 0:  # the draw fell beyond the last action with mass through rounding
+            action -= 1
+        if step_env:
+            env.step(action)
+        return action, (probs if need_probs else None)
+
     def update_weights(self, weights_for_eval_agent):
         raise NotImplementedError
 
     # ---- state
     def set_stack_size(self, stack_size):
         self._stack_size = stack_size
+        self._internal_env = None  # rebuilt with the new stacks on next use
 
     def get_mode(self):
         return self._mode
