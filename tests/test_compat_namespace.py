@@ -19,3 +19,18 @@ def test_example_imports_resolve_to_b200_implementation():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "pokerrl_b200", "compat"), ROOT]))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_evaluator_modules_resolve():
+    """the evaluator side of the plugin surface: PokerRL.eval.{br,lbr}, PokerRange, EvalAgentBase"""
+    code = ("from PokerRL.eval.lbr.LocalLBRWorker import LocalLBRWorker\n"
+            "from PokerRL.eval.lbr.LBRArgs import LBRArgs\n"
+            "from PokerRL.eval.br.LocalBRMaster import LocalBRMaster\n"
+            "from PokerRL.game.PokerRange import PokerRange\n"
+            "from PokerRL.rl.base_cls.EvalAgentBase import EvalAgentBase\n"
+            "import pokerrl_b200.eval.lbr.LocalLBRWorker as m\n"
+            "assert LocalLBRWorker is m.LocalLBRWorker and LBRArgs(lbr_check_to_round=1).lbr_check_to_round == 1\n"
+            "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "pokerrl_b200", "compat"), ROOT]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
