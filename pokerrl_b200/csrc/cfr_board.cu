@@ -53,20 +53,14 @@ static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move mult
 #define PRL_BV_RED 1         // chance sums by 64-bit RED instead of load + add + store
 #endif
 #ifndef PRL_BV_P1PIPE
-#define PRL_BV_P1PIPE 1      // P1 rows: 1 / 2 = only the first (two) position(s) requested one unit ahead, the rest inside P1; 0 = all three
+#define PRL_BV_P1PIPE 1      // P1 rows: 1 = only the first position requested one unit ahead, the rest inside P1; 0 = all three
 #endif
 #ifndef PRL_BV_FOLDLIN
 #define PRL_BV_FOLDLIN 1     // update form: card-row sums of the fold vectors from the showdown vectors' row totals (linearity)
 #endif
-#ifndef PRL_BV_SCAN7
-#define PRL_BV_SCAN7 0       // main prefix sums by five warps (the lighter card-row group), seven consecutive positions per thread
-#endif                       // (measured: 89.7 vs 92.4 it/s - idle warps cost more than the shuffles they save)
 #ifndef PRL_BV_ERT
 #define PRL_BV_ERT 1         // card-row prefix arrays entry-major (Er[v][k][card]) instead of card-major: fewer store conflicts in P2a
 #endif
-#ifndef PRL_BV_P3BAL
-#define PRL_BV_P3BAL 0       // P3: the 313 positions of the third pass spread over all twelve warps (27 lanes each)
-#endif                       // (measured: 91.0 vs 92.2 it/s)
 #ifndef PRL_BV_ROWTOTF
 #define PRL_BV_ROWTOTF 1     // kLin: a lane's part of a card row's total summed in float (12 terms), only the quad reduction in double
                              // (measured: +1 %, parity unchanged at <= 1.6e-7)
@@ -74,11 +68,10 @@ static_assert(kBlobA % 16 == 0 && kRowIdxBytes % 16 == 0, "bulk copies move mult
 #ifndef PRL_BV_NEWTON
 #define PRL_BV_NEWTON 1      // regret matching: Newton step after MUFU.RCP (<= 1 ulp); 0 = the approximation as is (2^-23 relative)
 #endif
-#ifndef PRL_BV_SPLITB3
-#define PRL_BV_SPLITB3 0     // the single-warp stage between B2 and B3 spread over nine warps (one vector / fold vector each)
-#endif                       // (measured: 89.0 vs 92.2 it/s)
 constexpr int kVP1Pipe = PRL_BV_P1PIPE;
-constexpr bool kVRed = PRL_BV_RED, kVFoldLin = PRL_BV_FOLDLIN, kVScan7 = PRL_BV_SCAN7, kVSplitB3 = PRL_BV_SPLITB3, kVErT = PRL_BV_ERT, kVP3Bal = PRL_BV_P3BAL;
+constexpr bool kVRed = PRL_BV_RED, kVFoldLin = PRL_BV_FOLDLIN, kVErT = PRL_BV_ERT;
+// measured and removed (profiles/r02_q_sweep_variants.md): five-warp / one-warp-per-vector scans, the single-warp stage spread
+// over nine warps, the third P3 pass spread over all warps, two positions requested a unit ahead
 
 constexpr int kThreads = 384;  // 12 warps; 3 strength positions per thread (3 * 384 = 1152 >= 1081: 94 % of the lanes busy)
 constexpr int kPerThread = 3;
@@ -396,12 +389,6 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             p1_load_k(j, sh, 2, gC, xC);
             p1_hand(1, gB, xB);
             p1_hand(2, gC, xC);
-        } else if constexpr (kVP1Pipe == 2) {  // the third position's rows have two hands' worth of work to arrive
-            float gC[NOPP], xC = 0.0f;
-            p1_load_k(j, sh, 2, gC, xC);
-            p1_hand(0, p1_g[0], p1_x0[0]);
-            p1_hand(1, p1_g[1], p1_x0[1]);
-            p1_hand(2, gC, xC);
         } else {
 #pragma unroll
             for (int k = 0; k < kPerThread; ++k) p1_hand(k, p1_g[k], p1_x0[k]);
@@ -415,9 +402,8 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // fold vectors: the row's mass cs[f][lc].  Two groups of 47 quads share the nine vectors (SD 0-2 + fold 0-1 | SD 3-4 +
         // fold 2-3); the other threads start on the main scans, which only read S as well.
         mbar_wait(&bars[2], it & 1);
-        constexpr int NLEG = kVScan7 ? 1 : NSD;  // registers of the thread-per-three-positions scan (legacy variant)
-        float a0[NLEG], a1[NLEG], a2[NLEG];
-        double pre[NLEG];
+        float a0[NSD], a1[NSD], a2[NSD];
+        double pre[NSD];
         constexpr int kQuadThreads = kLiveCards * 4;  // 188
         if (warp < (2 * kQuadThreads + 31) / 32) {   // whole warps (the quad shuffles name every lane)
             const int grp = (tid >= kQuadThreads) ? 1 : 0;
@@ -478,37 +464,11 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         // ------------------------------------------------------------------------------------------ P2b: main scans, part 1
         // centred exclusive prefix sums over the strength order: E[k] = (mass of the k weakest hands) - total / 2, k = 0 ..
         // 1081, sums in double (the showdown value is a difference of two prefixes).
-        // kVScan7: by the five warps 7..11 only - the card-row group with two vectors instead of three, so the two groups
-        // finish P2 together - thread t owns the seven consecutive positions 7 t .. 7 t + 6 (odd stride: conflict-free):
-        // 5 / 12 of the shuffles of the thread-per-three-positions scan, and after B2 every scan warp adds the totals of the
-        // warps below it itself (the single-warp scan of the warp totals and its barrier are gone).
-        constexpr int kScanWarp0 = 7, kScanWarps = kWarps - kScanWarp0, kScanPer = 7;
-        static_assert(kScanWarps * 32 * kScanPer > kLive + 1 && (kScanPer & 1), "scan geometry");
-        const bool scan_warp = kVScan7 && warp >= kScanWarp0;
-        double pre7[kVScan7 ? NSD : 1];
-        if constexpr (kVScan7) {
-            if (scan_warp) {
-                const int b0 = kScanPer * (tid - kScanWarp0 * 32);
-#pragma unroll
-                for (int v = 0; v < NSD; ++v) {
-                    const float* Sv = S + v * kLdb;
-                    double loc = 0.0;
-#pragma unroll
-                    for (int e = 0; e < kScanPer; ++e) loc += (b0 + e < kLive) ? (double)Sv[b0 + e] : 0.0;
-                    double incw = loc;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const double tt = __shfl_up_sync(0xffffffffu, incw, o);
-                        if (lane >= o) incw += tt;
-                    }
-                    pre7[v] = incw - loc;  // exclusive within the warp
-                    if (lane == 31) wsum[v * 16 + (warp - kScanWarp0)] = incw;
-                }
-            }
-        } else {
+        // Thread t owns positions 3t .. 3t+2.
+        {
             const int b0 = 3 * tid;
 #pragma unroll
-            for (int v = 0; v < NLEG; ++v) {
+            for (int v = 0; v < NSD; ++v) {
                 const float* Sv = S + v * kLdb;
                 a0[v] = (b0 < kLive) ? Sv[b0] : 0.0f;
                 a1[v] = (b0 + 1 < kLive) ? Sv[b0 + 1] : 0.0f;
@@ -530,13 +490,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
         const float* own_rows = tab_own + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb;
         float* reg_rows = G.regret + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb;
         float* avg_rows = G.avg + (size_t)j * kBoardFloats + (size_t)OWN0 * kLdb;
-        // strength position of the thread's k-th hand of P3.  kVP3Bal: the last pass has only 1081 - 768 = 313 positions - ten
-        // warps' worth, two warps would idle at the unit's last barrier - so every warp takes 27 of them
-        constexpr int kP3Last = (kLive - 2 * kThreads + kWarps - 1) / kWarps;  // 27
-        auto p3_pos = [&](int k) -> int {
-            if (kVP3Bal && k == 2) return (lane < kP3Last) ? 2 * kThreads + warp * kP3Last + lane : kLdb;
-            return tid + k * kThreads;
-        };
+        auto p3_pos = [&](int k) -> int { return tid + k * kThreads; };  // strength position of the thread's k-th hand of P3
         float gA[NOWN], aA[NOWN], gB[NOWN], aB[NOWN];
         auto p3_load = [&](int k, float (&g)[NOWN], float (&av)[NOWN]) {
             const int i = min(p3_pos(k), kLive - 1);  // unconditional (see p1_load_k)
@@ -583,36 +537,7 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
             if (lane < kLiveCards) cs[f * kRowPad + lane] = (float)c0;  // float copies for the per-hand epilogue
             if (lane + 32 < kLiveCards) cs[f * kRowPad + lane + 32] = (float)c1;
         };
-        if constexpr (kVScan7) {
-            if (scan_warp) {  // offsets from the warp totals (written before B2), then the prefixes in place
-                const int b0 = kScanPer * (tid - kScanWarp0 * 32), sw = warp - kScanWarp0;
-#pragma unroll
-                for (int v = 0; v < NSD; ++v) {
-                    double below = 0.0, total = 0.0;
-#pragma unroll
-                    for (int w = 0; w < kScanWarps; ++w) {
-                        const double t = wsum[v * 16 + w];
-                        total += t;
-                        below += (w < sw) ? t : 0.0;
-                    }
-                    float* Sv = S + v * kLdb;
-                    double run = (pre7[v] + below) - 0.5 * total;
-#pragma unroll
-                    for (int e = 0; e < kScanPer; ++e) {
-                        const int p = b0 + e;
-                        if (p <= kLive) {
-                            const float xv = (p < kLive) ? Sv[p] : 0.0f;
-                            Sv[p] = (float)run;
-                            run += (double)xv;
-                        }
-                    }
-                }
-            } else if (warp < NF) {
-                static_for<0, NF>([&](auto F) {
-                    if (warp == decltype(F)::value) fold_finish(F);
-                });
-            }
-        } else {
+        {
             auto warp_totals_scan = [&](int v) {  // exclusive scan of the 12 warp totals of vector v
                 const double w = (lane < kWarps) ? wsum[v * 16 + lane] : 0.0;
                 double sc = w;
@@ -624,25 +549,16 @@ __global__ void __launch_bounds__(kThreads, 2) board_sweep_kernel(const SweepArg
                 const double total = __shfl_sync(0xffffffffu, sc, kWarps - 1);
                 if (lane < kWarps) wexc[v * 16 + lane] = (sc - w) - 0.5 * total;
             };
-            if constexpr (kVSplitB3) {  // nine short chains side by side instead of two long ones
-                static_assert(NLEG + NF <= kWarps, "one warp per vector");
-                if (warp < NLEG) {
-                    warp_totals_scan(warp);
-                } else if (warp < NLEG + NF) {
-                    static_for<0, NF>([&](auto F) {
-                        if (warp - NLEG == decltype(F)::value) fold_finish(F);
-                    });
-                }
-            } else if (warp == 0) {
+            if (warp == 0) {
 #pragma unroll
-                for (int v = 0; v < NLEG; ++v) warp_totals_scan(v);
+                for (int v = 0; v < NSD; ++v) warp_totals_scan(v);
             } else if (warp == 1) {
                 static_for<0, NF>([&](auto F) { fold_finish(F); });
             }
             __syncthreads();  // B3
             const int b0 = 3 * tid;
 #pragma unroll
-            for (int v = 0; v < NLEG; ++v) {
+            for (int v = 0; v < NSD; ++v) {
                 float* Sv = S + v * kLdb;
                 double run = pre[v] + wexc[v * 16 + warp];
                 if (b0 <= kLive) Sv[b0] = (float)run;

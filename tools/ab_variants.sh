@@ -1,9 +1,9 @@
 #!/bin/bash
-# A/B of the board sweep variants on the full game (run on the GPU box): tools/ab_variants.sh [variants...]
-# writes gpurun_out/ab_variants.jsonl (one board_probe line per variant) and runs the board-engine parity tests on "all"
+# A/B of the board sweep switches on the full game (run on the GPU box after tools/build_variants.py): tools/ab_variants.sh [variants...]
+# writes gpurun_out/ab_variants.jsonl (one board_probe line per variant)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-V=${@:-base red p1pipe foldlin serialscan all_noscan all}
+V=${@:-base final}
 : > gpurun_out/ab_variants.jsonl
 for v in $V; do
   echo -n "{\"variant\": \"$v\", \"probe\": " >> gpurun_out/ab_variants.jsonl

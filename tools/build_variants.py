@@ -9,22 +9,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pokerrl_b200.csrc import build as B  # noqa: E402
 
+# switches left in csrc/cfr_board.cu: each accepted change against its predecessor (the rejected ones were removed from the
+# source; profiles/r02_q_sweep_variants.md keeps their numbers)
+_ON = dict(RED=1, P1PIPE=1, FOLDLIN=1, ERT=1, ROWTOTF=1, NEWTON=1)
 VARIANTS = {
-    "base": dict(RED=0, P1PIPE=0, FOLDLIN=0, SCAN7=0, SPLITB3=0),
-    "red": dict(RED=1, P1PIPE=0, FOLDLIN=0, SCAN7=0, SPLITB3=0),
-    "p1pipe": dict(RED=0, P1PIPE=1, FOLDLIN=0, SCAN7=0, SPLITB3=0),
-    "foldlin": dict(RED=0, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0),
-    "noscan": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0),
-    "scan7": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=1, SPLITB3=0),
-    "splitb3": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=1),
-    "ert": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
-    "splitb3_ert": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=1, ERT=1),
-    "final": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
-    "rowtotf": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1, ROWTOTF=1),
-    "nonewton": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1, NEWTON=0),
-    "ert_p1a2": dict(RED=1, P1PIPE=2, FOLDLIN=1, SCAN7=0, SPLITB3=0, ERT=1),
-    "p3bal": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=0, P3BAL=1),
-    "splitb3_ert_p3bal": dict(RED=1, P1PIPE=1, FOLDLIN=1, SCAN7=0, SPLITB3=1, ERT=1, P3BAL=1),
+    "final": dict(_ON),
+    "base": dict(RED=0, P1PIPE=0, FOLDLIN=0, ERT=0, ROWTOTF=0, NEWTON=1),
+    "no_red": dict(_ON, RED=0),
+    "no_p1pipe": dict(_ON, P1PIPE=0),
+    "no_foldlin": dict(_ON, FOLDLIN=0),
+    "no_ert": dict(_ON, ERT=0),
+    "no_rowtotf": dict(_ON, ROWTOTF=0),
+    "no_newton": dict(_ON, NEWTON=0),
 }
 
 
