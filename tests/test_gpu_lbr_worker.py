@@ -57,3 +57,47 @@ def test_reference_lbr_episodes_replay(game_name):
     print("%s: %d hands, %d LBR decisions replayed; utilities within %.1e of the reference's; winnings mismatches: %s"
           % (game_name, len(decks), n_dec, worst, mism))
     assert not mism and worst <= 1e-4 and n_dec > 50  # measured: Flop5Holdem (complete boards) ~1e-7, NL flop / turn roll-outs 3.3e-5
+
+
+def test_lbr_master_logs_mean_and_confidence_interval():
+    """LocalLBRMaster with one local worker: n hands per seat with fresh deals, mean and the 95 % bounds logged under the
+    reference's experiment names (EvaluatorMasterBase.py:83-128); the policy agent samples with numpy's global RNG"""
+    import numpy as np
+    from lbr_common import policy_table
+    from pokerrl_b200.eval.lbr.LBRArgs import LBRArgs
+    from pokerrl_b200.eval.lbr.LocalLBRMaster import LocalLBRMaster
+    from pokerrl_b200.eval.lbr.LocalLBRWorker import LocalLBRWorker
+    from pokerrl_b200.game import games
+    from pokerrl_b200.game.Poker import Poker
+    from pokerrl_b200.rl.base_cls.EvalAgentBase import EvalAgentBase
+    from pokerrl_b200.rl.base_cls.TrainingProfileBase import TrainingProfileBase
+    from pokerrl_b200.rl.base_cls.workers.ChiefBase import ChiefBase
+
+    class Agent(EvalAgentBase):
+        ALL_MODES = ["table"]
+
+        def can_compute_mode(self):
+            return True
+
+        def update_weights(self, w):
+            pass
+
+        def get_a_probs_for_each_hand(self):
+            env = self.internal_env
+            return policy_table(self.env_bldr.rules.RANGE_SIZE, self.env_bldr.N_ACTIONS, env.get_legal_actions(), env.current_round)
+
+    t_prof = TrainingProfileBase("m", games.Flop5Holdem, [1.0], eval_stack_sizes=[[20000, 20000]], eval_modes_of_algo=("table",))
+    t_prof.module_args["lbr"] = LBRArgs(n_lbr_hands_per_seat=30, lbr_check_to_round=Poker.FLOP)
+    chief = ChiefBase(t_prof=None)
+    chief.pull_current_eval_strategy = lambda info: (None, info)
+    master = LocalLBRMaster(t_prof=t_prof, chief_handle=chief)
+    master.set_worker_handles(LocalLBRWorker(t_prof=t_prof, chief_handle=chief, eval_agent_cls=Agent))
+    np.random.seed(3)
+    master.update_weights()
+    master.evaluate(iter_nr=7)
+    exps = chief.get_experiments()
+    g = "Evaluation/" + games.Flop5Holdem.WIN_METRIC
+    total = exps["m table_stack_20000: LBR Total"][g]
+    lo, hi = exps["m table_stack_20000: LBR Conf_lower95"][g], exps["m table_stack_20000: LBR Conf_upper95"][g]
+    assert total[0][0] == 7 and lo[0][1] <= total[0][1] <= hi[0][1] and hi[0][1] > lo[0][1]
+    print("LBR master: %.1f [%0.1f, %0.1f] %s over 60 hands" % (total[0][1], lo[0][1], hi[0][1], games.Flop5Holdem.WIN_METRIC))
