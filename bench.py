@@ -187,6 +187,40 @@ def run_cpu_fhp(n_boards, n_iters, threads):
     return sec, c.n_threads, c.exploitability_current()
 
 
+HULH_CPU_CARDS = (1, 8)  # matched CPU / GPU instance of the hulh workload: the first turn card x the first 8 river cards
+
+
+def hulh_subgame_tree(turn_cards, river_cards):
+    """flat tree + constructor arguments of the Limit Hold'em flop sub-game restricted to the first n turn / river cards"""
+    from pokerrl_b200.game import games
+    from pokerrl_b200.game.flat_tree import FlatTree
+    from pokerrl_b200.game.holdem_boards import MultiStreetBoards
+    g = games.LimitHoldem
+    args = g.ARGS_CLS(n_seats=2, starting_stack_sizes_list=[48, 48], bet_sizes_list_as_frac_of_pot=[1.0])
+    free = [c for c in range(52) if c not in HULH_FLOP]
+    spec = MultiStreetBoards.subgame(g.RULES, HULH_FLOP, 2, 1, cards_per_layer=[free[:turn_cards], free[:river_cards + turn_cards]])
+    return g, args, spec, FlatTree(g, args, board_spec=spec, root_actions=[1, 1])
+
+
+def run_cpu_hulh(n_iters, threads):
+    """oracle/cfr2_oracle.c (float64, OpenMP) Linear CFR on the matched hulh instance: (seconds per iteration, threads,
+    river boards of the instance, exploitability mbb/g)"""
+    import numpy as np
+    import cfr2_c
+    from twocard_common import oracle_ranks
+    g, args, spec, ft = hulh_subgame_tree(*HULH_CPU_CARDS)
+    bc = ft.board_cards()
+    ranks = np.full((bc.shape[0], ft.R), -1, np.int32)
+    complete = np.nonzero((bc >= 0).sum(axis=1) == 5)[0]
+    ranks[complete] = oracle_ranks(bc[complete])
+    c = cfr2_c.Oracle2CSolver(ft, ranks, "LinearCFR", n_threads=min(threads, 16), lean=True, ev_normalizer=g.EV_NORMALIZER)
+    c.iteration(2)  # first touch of the node arrays
+    t0 = time.perf_counter()
+    c.iteration(n_iters)
+    sec = (time.perf_counter() - t0) / n_iters
+    return sec, c.n_threads, int(complete.size), c.exploitability_current()
+
+
 def run_aux(a):
     """BASELINE.json configs[4]: 2^20 parallel heads-up DiscretizedNLHoldem tables (bet_sets.B_5, stacks 20000, uniformly
     random legal actions from the counter RNG, finished hands re-dealt) and batched 7-card evaluation throughput."""
@@ -942,7 +976,29 @@ def main():
     if world == 1 and not a.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
         if hulh:
-            pass
+            # matched instance (first turn card x 8 river cards) on both sides; the CPU figure scaled by the river-board count
+            g2, args2, spec2, _ = hulh_subgame_tree(*HULH_CPU_CARDS)
+            small = ShardedCFRSolver(g2, args2, spec2, "LinearCFR", device=dev, root_actions=[1, 1])
+            small.iteration(3)
+            torch.cuda.synchronize()
+            e0m, e1m = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0m.record()
+            small.iteration(20)
+            e1m.record()
+            torch.cuda.synchronize()
+            gpu_its = 20e3 / e0m.elapsed_time(e1m)
+            sec, threads, n_river_small, _ = run_cpu_hulh(4, ncpu)
+            n_river = int(sum(1 for _ in range(len(spec.boards[2]))))
+            out["matched_instance"] = {"turn_x_river_cards": list(HULH_CPU_CARDS), "river_boards": n_river_small,
+                                       "gpu_iterations_per_s": gpu_its, "cpu_iterations_per_s": 1.0 / sec, "cpu_threads": threads,
+                                       "same_config": True, "ratio": gpu_its * sec}
+            out["cpu_baseline"] = {"value": 1.0 / (sec * n_river / n_river_small), "unit": "iterations/s", "cores": threads,
+                                   "kind": "port",
+                                   "sample": "4 Linear-CFR iterations of oracle/cfr2_oracle.c (float64, OpenMP, %d threads) on the "
+                                             "sub-game restricted to %d turn x %d river cards (%d river boards) at %.4f s/iteration, "
+                                             "scaled by the river-board count (%d here) - the cost is dominated by the river rounds; "
+                                             "the reference cannot run Hold'em trees at all (SURVEY.md headline 2)"
+                                             % (threads, HULH_CPU_CARDS[0], HULH_CPU_CARDS[1], n_river_small, sec, n_river)}
         else:
             n = max(2, min(K, int(15.0 / max(0.014 * st["nodes"] / 873586.0, 1e-4))))
             n = (n // a.eval_every) * a.eval_every or n
