@@ -18,7 +18,8 @@ def _stream(dev):
 
 
 class AllinEquity:
-    def __init__(self, rules, spec=None, device=None, ranks=None, chunk=16384, boards=None, weights=None, sym_perm=None):
+    def __init__(self, rules, spec=None, device=None, ranks=None, chunk=16384, boards=None, weights=None, sym_perm=None,
+                 keep_ec=False):
         """spec: holdem_boards.BoardSpec (boards, board_prob, board_mult, sym_perm) - or boards int8 [n, 5], weights
         float64 [n] (deal probability x weight in the parent's sum) and sym_perm given directly; ranks: optional DEVICE
         int32 [n_boards, R] hand strengths of the boards (else computed here by prl_hand_rank_boards)."""
@@ -49,7 +50,7 @@ class AllinEquity:
             nat.call("prl_allin_equity_finish", C.c_void_p(ec.data_ptr()), R, C.c_void_p(self.hand_cards.data_ptr()),
                      C.c_void_p(self.sym.data_ptr()) if self.sym is not None else None,
                      int(sp.shape[0]) if sp is not None else 0, C.c_void_p(self.tiles.data_ptr()), _stream(dev))
-            self.ec = ec  # unsymmetrised float64 sums (kept for inspection / tests; 14 MB)
+            self.ec = ec if keep_ec else None  # unsymmetrised float64 sums (14 MB): kept on request (inspection / tests)
 
     def values(self, x, scale=None, out=None):
         """y[c] = scale[c] * E @ x[c] for the rows of x (float32 [n_cols, ld >= R], device) - one tensor-core launch per 16 rows"""

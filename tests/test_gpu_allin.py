@@ -37,7 +37,7 @@ def test_equity_matrix_and_dense_rows_on_reference_ranks():
     boards, ranks = GOLD["boards"], GOLD["ranks"]
     w = (np.arange(len(boards)) % 16 + 8.0) / 64.0
     spec = BoardSpec(boards, w, np.ones(len(boards)), None, "golden boards")
-    eq = AllinEquity(rules, spec, chunk=64)
+    eq = AllinEquity(rules, spec, chunk=64, keep_ec=True)
     E64 = o2.allin_equity_matrix(ranks, w, hc, 52)
     inc = np.zeros((1326, 52))
     inc[np.arange(1326), hc[:, 0]] = 1
